@@ -1,0 +1,152 @@
+/*
+ * macroc_b200.h -- C ABI of the B200 (sm_100a) implementation of MacroC's
+ * macro-scale FE hot path.
+ *
+ * The reference (GG1991/macroc) has no plugin/FFI layer: its hot path is a
+ * handful of C functions that take PETSc handles and read file-scope globals
+ * (reference include/macroc.h:71-155).  This header is the drop-in boundary
+ * for that path: one opaque context replaces the globals, and there is one
+ * entry point per reference function.  Plain C types only; every function
+ * returns a PetscErrorCode-style int (0 = success) and never throws.  One host
+ * thread/process per GPU, like one MPI rank per DMDA sub-box in the reference.
+ *
+ * Vector layout at the boundary is the reference's: PETSc DMDA "natural"
+ * ordering restricted to the rank's owned z-slab, dof-interleaved:
+ *     v[3*((i) + NX*((j) + NY*(k - zs))) + d],  zs <= k < zs + nz_owned.
+ * (With -da_processors_x 1 -da_processors_y 1 -da_processors_z P, PETSc's
+ * global ordering coincides with the natural one.)
+ *
+ * There is no CPU fallback: every compute entry point fails with
+ * MACROC_ERR_NO_DEVICE when no CUDA device is usable.
+ */
+#ifndef MACROC_B200_H
+#define MACROC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MACROC_OK                0
+#define MACROC_ERR_ARG          62   /* PETSC_ERR_ARG_WRONG  */
+#define MACROC_ERR_UNSUPPORTED  56   /* PETSC_ERR_SUP        */
+#define MACROC_ERR_MEM          55   /* PETSC_ERR_MEM        */
+#define MACROC_ERR_NO_DEVICE    97
+#define MACROC_ERR_CUDA         98
+#define MACROC_ERR_NCCL         99
+
+enum { MACROC_BC_BENDING = 0, MACROC_BC_CIRCLE = 1 };          /* include/macroc.h:58 */
+enum { MACROC_VEC_U = 0, MACROC_VEC_DU = 1, MACROC_VEC_B = 2 }; /* include/macroc.h:128 */
+enum { MACROC_OP_ASSEMBLED = 0, MACROC_OP_MATRIX_FREE = 1 };
+/* KSPConvergedReason values used */
+enum {
+    MACROC_KSP_CONVERGED_RTOL = 2, MACROC_KSP_CONVERGED_ATOL = 3,
+    MACROC_KSP_DIVERGED_ITS = -3, MACROC_KSP_DIVERGED_DTOL = -4,
+    MACROC_KSP_DIVERGED_INDEFINITE_MAT = -10
+};
+
+/* Everything init() fixes (reference src/init.c:47-64,66-83,85-94,137-157). */
+typedef struct {
+    int32_t NX, NY, NZ;            /* -da_grid_x/y/z          (macroc.h:44-46: 40, 3, 40)   */
+    int32_t px, py, pz;            /* -da_processors_x/y/z; this build shards z-slabs only:
+                                      px = py = 1 (0 = decide = 1), pz = 0 -> nranks         */
+    double  lx, ly, lz;            /* -lx -ly -lz             (macroc.h:47-49: 50, 1, 50)   */
+    int32_t bc_type;               /* -bc_type                (init.c:64: BC_CIRCLE)        */
+    int32_t ts;                    /* -ts                     (macroc.h:41: 1)              */
+    double  dt, final_time;        /* -dt                     (macroc.h:43,40)              */
+    int32_t newton_max_its;        /* -newton_max_its | -new_its (macroc.h:38: 5)           */
+    double  newton_min_tol;        /* -newton_min_tol | -new_tol (macroc.h:37: 1e-1)        */
+    double  newton_rel_tol;        /* -newton_rel_tol         (macroc.h:36: 1e-4)           */
+    double  ksp_rtol, ksp_abstol, ksp_dtol;   /* init.c:147: 1e-5, 1e-50, 1e4               */
+    int32_t ksp_maxits;            /* init.c:148: 10000                                      */
+    double  E, nu;                 /* -micro_mat_1 E,nu,..    (init.c:31: 1e7, 0.25)        */
+    double  D[36];                 /* homogenised tangent, row-major 6x6, Voigt order
+                                      (e11 e22 e33 g12 g13 g23); used if use_D != 0          */
+    int32_t use_D;
+    int32_t op;                    /* MACROC_OP_ASSEMBLED (reference: MATAIJ + MatMult) or
+                                      MACROC_OP_MATRIX_FREE for solve_Ax                     */
+    int32_t device;                /* CUDA device ordinal, -1 = current                      */
+    int32_t reserved[8];
+} macroc_config;
+
+typedef struct macroc_ctx macroc_ctx;
+
+/* ---- setup (init.c:25-219 / finish :222-237) ------------------------------ */
+int macroc_default_config(macroc_config *cfg);
+/* Parses MacroC's/PETSc's command-line keys into cfg (init.c:66-83 and the
+ * -da_* / -ksp_* keys DMSetFromOptions/KSPSetFromOptions read, init.c:93,156).
+ * README's -new_its/-new_tol are accepted as aliases. Unknown keys are ignored,
+ * like the PETSc options database does. */
+int macroc_config_from_args(macroc_config *cfg, int argc, const char *const *argv);
+/* 128-byte NCCL unique id for multi-rank contexts; rank 0 creates it, the host
+ * ships it to the other ranks by any means (file, torch.distributed, MPI). */
+int macroc_get_unique_id(void *id128);
+int macroc_create(const macroc_config *cfg, int rank, int nranks, const void *id128,
+                  macroc_ctx **out);
+int macroc_destroy(macroc_ctx *ctx);
+const char *macroc_last_error(const macroc_ctx *ctx);   /* ctx may be NULL */
+
+/* ---- host-only partition queries (no GPU needed) --------------------------- */
+/* DMDA ownership of `rank` (PETSc: M/m + ((M%m) > i)), its ghost corners and
+ * element counts (DMDAGetCorners / GetGhostCorners / GetElementsSizes as used
+ * at init.c:167-171).  out[15] = xs,ys,zs,xm,ym,zm, Xs,Ys,Zs,Xm,Ym,Zm, nex,ney,nez */
+int macroc_partition(const macroc_config *cfg, int rank, int nranks, int32_t out[15]);
+/* bc_init (bcs.c:154-338): Dirichlet GLOBAL dof ids of this rank's ghosted box,
+ * -1 padded exactly like index_dirichlet; coef[i]*U is the value
+ * apply_bc_on_u (bcs.c:61-146) inserts.  Call with idx == NULL to get *n. */
+int macroc_bc_lists(const macroc_config *cfg, int rank, int nranks, int32_t *idx,
+                    double *coef, int32_t *n);
+
+/* ---- the hot path: one entry point per reference function ------------------ */
+double macroc_get_displacement(const macroc_ctx *ctx, int time_s);            /* bcs.c:52-58     */
+int macroc_apply_bc_on_u(macroc_ctx *ctx, double U);                          /* bcs.c:29-146    */
+/* set_strains (assembly.c:25-66).  Always refreshes the halo of u.  If
+ * materialize != 0 the Gauss-point strain and stress = D strain arrays
+ * (gpi = ie*8 + gp, assembly.c:58) are written to device memory for a
+ * constitutive plug-in / export; the residual kernel recomputes them in
+ * registers either way. */
+int macroc_set_strains(macroc_ctx *ctx, int materialize);
+int macroc_assembly_res(macroc_ctx *ctx, double *norm);    /* assembly.c:120-176 + VecNorm main.c:67 */
+int macroc_assembly_jac(macroc_ctx *ctx);                  /* assembly.c:69-117 + bcs.c:341-347      */
+int macroc_solve_Ax(macroc_ctx *ctx, int *its, double *rnorm);   /* assembly.c:179-192 (KSPCG+PCJACOBI) */
+int macroc_ksp_reason(const macroc_ctx *ctx, int *reason);
+int macroc_update_u(macroc_ctx *ctx);                      /* VecAXPY(u,1,du) main.c:79 */
+int macroc_calc_B(int gp, double *B /* [6][24] */);        /* assembly.c:195-254 (host, constants) */
+int macroc_calc_force(macroc_ctx *ctx, double *force);     /* forces.c:25-166 */
+
+/* One Newton loop of one time step (main.c:53-82) with the reference's
+ * control flow; res_norms gets the |RES| of every iteration (n_res of them),
+ * ksp_its the CG iteration count of every solve.  Arrays may be NULL. */
+int macroc_time_step(macroc_ctx *ctx, int time_s, int *newton_its, double *res_norms,
+                     int *n_res, int *ksp_its, double *ksp_rnorms);
+
+/* ---- vectors / matrix across the boundary ---------------------------------- */
+int64_t macroc_local_ndof(const macroc_ctx *ctx);          /* 3 * owned nodes            */
+int64_t macroc_global_ndof(const macroc_ctx *ctx);
+int macroc_set_vec(macroc_ctx *ctx, int which, const double *host);   /* H2D, owned slab */
+int macroc_get_vec(macroc_ctx *ctx, int which, double *host);         /* D2H, owned slab */
+/* Assembled operator as 27 3x3 blocks per owned node:
+ * out[((node*27 + slot)*9) + 3*r + c], slot = (dz+1)*9 + (dy+1)*3 + (dx+1). */
+int macroc_get_matrix_blocks(macroc_ctx *ctx, double *host);
+/* y = A x with the assembled (op = 0) or matrix-free (op = 1) operator; x, y on
+ * the host in boundary layout (halo exchanged internally). */
+int macroc_matmult(macroc_ctx *ctx, int op, const double *x_host, double *y_host);
+int macroc_get_strain_stress(macroc_ctx *ctx, double *strain, double *stress, int64_t *n_gp);
+
+/* ---- measurement hooks ------------------------------------------------------ */
+/* Runs `reps` launches of one kernel family on the context's stream with data
+ * already resident in HBM and returns the mean device time per launch in ms
+ * (CUDA events on that stream).  what: 0 SpMV assembled, 1 apply matrix-free,
+ * 2 one full PCG iteration (assembled), 3 Jacobian assembly, 4 residual,
+ * 5 one full PCG iteration (matrix-free).  flush_l2 != 0 writes a >L2 buffer
+ * between launches. */
+int macroc_time_kernel(macroc_ctx *ctx, int what, int reps, int flush_l2, double *ms_mean);
+uint64_t macroc_launch_count(const macroc_ctx *ctx);       /* kernels launched so far */
+int macroc_device_synchronize(macroc_ctx *ctx);
+int macroc_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,813 @@
+// capi.cu -- the C ABI of include/macroc_b200.h over the kernels in kernels.cuh.
+//
+// One macroc_ctx replaces the reference's file-scope globals
+// (include/macroc.h:71-128): it owns the slab's device vectors u, du, b, the
+// assembled operator, the Dirichlet bookkeeping and the KSP work vectors, a
+// CUDA stream and (for nranks > 1) an NCCL communicator used for the z-plane
+// halo exchange and the CG dot-product all-reduces.
+// No CPU fallback: compute entry points return MACROC_ERR_NO_DEVICE without a GPU.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+#include <nccl.h>
+
+#include "../../include/macroc_b200.h"
+#include "grid.h"
+#include "kernels.cuh"
+
+using namespace macroc;
+
+static thread_local std::string g_last_error;
+
+enum { V_U = 0, V_DU = 1, V_B = 2, V_R = 3, V_P = 4, V_W = 5, V_DINV = 6, V_COUNT = 7 };
+
+struct macroc_ctx {
+    macroc_config cfg;
+    Slab slab;
+    Geometry geo;
+    GridDev g;
+    int device = 0;
+    cudaStream_t stream = nullptr, comm_stream = nullptr;
+    cudaEvent_t ev_ready = nullptr, ev_halo = nullptr, ev_t0 = nullptr, ev_t1 = nullptr, ev_chk[2] = {nullptr, nullptr};
+    ncclComm_t comm = nullptr;
+    double *vec[V_COUNT] = {nullptr};
+    double2 *A = nullptr;
+    bool A_valid = false, mf_ready = false;
+    double *Ke = nullptr, *T = nullptr;
+    uint8_t *nodemask = nullptr;
+    int64_t *bc_idx = nullptr;
+    double *bc_coef = nullptr;
+    int nbc = 0;
+    double *partial = nullptr;
+    int partial_cap = 0;
+    double *sums = nullptr;          // device: 4 doubles
+    double *sums_host = nullptr;     // pinned: 4 doubles
+    CgScalars *sc = nullptr;         // device
+    CgScalars *sc_host = nullptr;    // pinned [2]
+    double *stage = nullptr;         // device staging, 3*nloc doubles (boundary layout)
+    double *strain = nullptr, *stress = nullptr;
+    double *flush = nullptr;
+    size_t flush_bytes = 0;
+    uint64_t launches = 0;
+    int ksp_reason = 0;
+    int vec_blocks = 0, spmv_blocks = 0;
+    std::string err;
+};
+
+#define FAIL(ctx, code, ...)                                   \
+    do {                                                       \
+        char _b[512];                                          \
+        snprintf(_b, sizeof(_b), __VA_ARGS__);                 \
+        g_last_error = _b;                                     \
+        if (ctx) (ctx)->err = _b;                              \
+        return (code);                                         \
+    } while (0)
+
+#define CU(ctx, call)                                                                       \
+    do {                                                                                    \
+        cudaError_t _e = (call);                                                            \
+        if (_e != cudaSuccess)                                                              \
+            FAIL(ctx, MACROC_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(_e)); \
+    } while (0)
+
+#define NC(ctx, call)                                                                       \
+    do {                                                                                    \
+        ncclResult_t _e = (call);                                                           \
+        if (_e != ncclSuccess)                                                              \
+            FAIL(ctx, MACROC_ERR_NCCL, "%s:%d %s -> %s", __FILE__, __LINE__, #call, ncclGetErrorString(_e)); \
+    } while (0)
+
+#define LAUNCH(ctx, kernel, grid, block, ...)                         \
+    do {                                                              \
+        kernel<<<(grid), (block), 0, (ctx)->stream>>>(__VA_ARGS__);   \
+        (ctx)->launches++;                                            \
+    } while (0)
+
+static inline int cdiv64(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+extern "C" int macroc_version(void) { return 100; }
+
+extern "C" const char *macroc_last_error(const macroc_ctx *ctx)
+{
+    return ctx ? ctx->err.c_str() : g_last_error.c_str();
+}
+
+extern "C" int macroc_default_config(macroc_config *cfg)
+{
+    if (!cfg) return MACROC_ERR_ARG;
+    memset(cfg, 0, sizeof(*cfg));
+    cfg->NX = 40; cfg->NY = 3; cfg->NZ = 40;                 // macroc.h:44-46
+    cfg->lx = 50.; cfg->ly = 1.; cfg->lz = 50.;              // macroc.h:47-49
+    cfg->bc_type = MACROC_BC_CIRCLE;                         // init.c:64
+    cfg->ts = 1; cfg->dt = 0.001; cfg->final_time = 1.0;     // macroc.h:40-43
+    cfg->newton_max_its = 5; cfg->newton_min_tol = 1.0e-1; cfg->newton_rel_tol = 1.0e-4;   // macroc.h:36-38
+    cfg->ksp_rtol = 1.0e-5; cfg->ksp_abstol = 1.0e-50; cfg->ksp_dtol = 1.0e4; cfg->ksp_maxits = 10000;  // init.c:147-148
+    cfg->E = 1.0e7; cfg->nu = 0.25;                          // init.c:31
+    cfg->op = MACROC_OP_ASSEMBLED;
+    cfg->device = -1;
+    return MACROC_OK;
+}
+
+extern "C" int macroc_config_from_args(macroc_config *cfg, int argc, const char *const *argv)
+{
+    if (!cfg) return MACROC_ERR_ARG;
+    for (int i = 0; i + 1 < argc; ++i) {
+        const char *k = argv[i], *v = argv[i + 1];
+        if (!k || k[0] != '-') continue;
+        auto is = [&](const char *name) { return strcmp(k, name) == 0; };
+        if (is("-da_grid_x")) cfg->NX = atoi(v);
+        else if (is("-da_grid_y")) cfg->NY = atoi(v);
+        else if (is("-da_grid_z")) cfg->NZ = atoi(v);
+        else if (is("-da_processors_x")) cfg->px = atoi(v);
+        else if (is("-da_processors_y")) cfg->py = atoi(v);
+        else if (is("-da_processors_z")) cfg->pz = atoi(v);
+        else if (is("-dt")) cfg->dt = atof(v);
+        else if (is("-lx")) cfg->lx = atof(v);
+        else if (is("-ly")) cfg->ly = atof(v);
+        else if (is("-lz")) cfg->lz = atof(v);
+        else if (is("-ts")) cfg->ts = atoi(v);
+        else if (is("-newton_min_tol") || is("-new_tol")) cfg->newton_min_tol = atof(v);
+        else if (is("-newton_rel_tol")) cfg->newton_rel_tol = atof(v);
+        else if (is("-newton_max_its") || is("-new_its")) cfg->newton_max_its = atoi(v);
+        else if (is("-bc_type")) cfg->bc_type = atoi(v);
+        else if (is("-ksp_rtol")) cfg->ksp_rtol = atof(v);
+        else if (is("-ksp_atol")) cfg->ksp_abstol = atof(v);
+        else if (is("-ksp_divtol")) cfg->ksp_dtol = atof(v);
+        else if (is("-ksp_max_it")) cfg->ksp_maxits = atoi(v);
+        else if (is("-micro_mat_1")) {                       // E,nu,Ka,Sy (init.c:82)
+            double a = 0, b = 0;
+            if (sscanf(v, "%lf,%lf", &a, &b) == 2) { cfg->E = a; cfg->nu = b; }
+        } else if (is("-mat_free")) cfg->op = atoi(v) ? MACROC_OP_MATRIX_FREE : MACROC_OP_ASSEMBLED;
+        else if (is("-ksp_type")) { if (strcmp(v, "cg") != 0) return MACROC_ERR_UNSUPPORTED; }
+        else if (is("-pc_type")) { if (strcmp(v, "jacobi") != 0) return MACROC_ERR_UNSUPPORTED; }
+    }
+    return MACROC_OK;
+}
+
+extern "C" int macroc_partition(const macroc_config *cfg, int rank, int nranks, int32_t out[15])
+{
+    if (!cfg || !out) return MACROC_ERR_ARG;
+    Slab s;
+    int rc = make_slab(*cfg, rank, nranks, &s);
+    if (rc) return rc;
+    int32_t v[15] = {0, 0, s.zs, s.NX, s.NY, s.nzl, 0, 0, s.Zs, s.NX, s.NY, s.Zm, s.nex, s.ney, s.nez};
+    memcpy(out, v, sizeof(v));
+    return MACROC_OK;
+}
+
+extern "C" int macroc_bc_lists(const macroc_config *cfg, int rank, int nranks, int32_t *idx, double *coef, int32_t *n)
+{
+    if (!cfg || !n) return MACROC_ERR_ARG;
+    Slab s;
+    int rc = make_slab(*cfg, rank, nranks, &s);
+    if (rc) return rc;
+    std::vector<int32_t> ix;
+    std::vector<double> cf;
+    build_bc_lists(*cfg, s, ix, cf);
+    if (idx) memcpy(idx, ix.data(), sizeof(int32_t) * ix.size());
+    if (coef) memcpy(coef, cf.data(), sizeof(double) * cf.size());
+    *n = (int32_t)ix.size();
+    return MACROC_OK;
+}
+
+extern "C" int macroc_calc_B(int gp, double *B)
+{
+    // assembly.c:195-254 (host helper; the device keeps the same table in c_dsh)
+    if (gp < 0 || gp >= 8 || !B) return MACROC_ERR_ARG;
+    static const int sg[8][3] = {{-1, -1, -1}, {+1, -1, -1}, {+1, +1, -1}, {-1, +1, -1},
+                                 {-1, -1, +1}, {+1, -1, +1}, {+1, +1, +1}, {-1, +1, +1}};
+    const double c = 0.577350269189626;
+    memset(B, 0, sizeof(double) * 6 * 24);
+    for (int n = 0; n < 8; ++n) {
+        double fx = 1 + sg[n][0] * (sg[gp][0] * c), fy = 1 + sg[n][1] * (sg[gp][1] * c), fz = 1 + sg[n][2] * (sg[gp][2] * c);
+        double h0 = sg[n][0] * fy * fz / 8. * 2., h1 = sg[n][1] * fx * fz / 8. * 2., h2 = sg[n][2] * fx * fy / 8. * 2.;
+        B[0 * 24 + 3 * n + 0] = h0; B[1 * 24 + 3 * n + 1] = h1; B[2 * 24 + 3 * n + 2] = h2;
+        B[3 * 24 + 3 * n + 0] = h1; B[3 * 24 + 3 * n + 1] = h0;
+        B[4 * 24 + 3 * n + 0] = h2; B[4 * 24 + 3 * n + 2] = h0;
+        B[5 * 24 + 3 * n + 1] = h2; B[5 * 24 + 3 * n + 2] = h1;
+    }
+    return MACROC_OK;
+}
+
+extern "C" int macroc_get_unique_id(void *id128)
+{
+    if (!id128) return MACROC_ERR_ARG;
+    ncclUniqueId id;
+    ncclResult_t e = ncclGetUniqueId(&id);
+    if (e != ncclSuccess) { g_last_error = ncclGetErrorString(e); return MACROC_ERR_NCCL; }
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    memcpy(id128, &id, 128);
+    return MACROC_OK;
+}
+
+static void isotropic_D(double E, double nu, double *D)
+{
+    double lambda = E * nu / ((1. + nu) * (1. - 2. * nu));
+    double mu = E / (2. * (1. + nu));
+    memset(D, 0, 36 * sizeof(double));
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) D[i * 6 + j] = lambda + (i == j ? 2. * mu : 0.);
+    for (int i = 3; i < 6; ++i) D[i * 6 + i] = mu;
+}
+
+static int ctx_free(macroc_ctx *c)
+{
+    if (!c) return MACROC_OK;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->comm) ncclCommDestroy(c->comm);
+    for (int i = 0; i < V_COUNT; ++i) cudaFree(c->vec[i]);
+    cudaFree(c->A); cudaFree(c->Ke); cudaFree(c->T); cudaFree(c->nodemask); cudaFree(c->bc_idx); cudaFree(c->bc_coef);
+    cudaFree(c->partial); cudaFree(c->sums); cudaFree(c->sc); cudaFree(c->stage); cudaFree(c->strain); cudaFree(c->stress);
+    cudaFree(c->flush);
+    if (c->sums_host) cudaFreeHost(c->sums_host);
+    if (c->sc_host) cudaFreeHost(c->sc_host);
+    for (cudaEvent_t e : {c->ev_ready, c->ev_halo, c->ev_t0, c->ev_t1, c->ev_chk[0], c->ev_chk[1]})
+        if (e) cudaEventDestroy(e);
+    if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return MACROC_OK;
+}
+
+extern "C" int macroc_destroy(macroc_ctx *ctx) { return ctx_free(ctx); }
+
+extern "C" int macroc_create(const macroc_config *cfg, int rank, int nranks, const void *id128, macroc_ctx **out)
+{
+    if (!cfg || !out) FAIL((macroc_ctx *)nullptr, MACROC_ERR_ARG, "macroc_create: null argument");
+    *out = nullptr;
+    Slab slab;
+    int rc = make_slab(*cfg, rank, nranks, &slab);
+    if (rc) FAIL((macroc_ctx *)nullptr, rc, "macroc_create: unsupported decomposition (z-slabs only: px=py=1, pz=nranks<=NZ)");
+    if (cfg->bc_type != MACROC_BC_BENDING && cfg->bc_type != MACROC_BC_CIRCLE)
+        FAIL((macroc_ctx *)nullptr, MACROC_ERR_ARG, "macroc_create: bc_type must be 0 or 1");
+    if (nranks > 1 && !id128) FAIL((macroc_ctx *)nullptr, MACROC_ERR_ARG, "macroc_create: nranks > 1 needs a unique id");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        FAIL((macroc_ctx *)nullptr, MACROC_ERR_NO_DEVICE, "macroc_create: no CUDA device (this library has no CPU path)");
+    }
+    macroc_ctx *c = new macroc_ctx();
+    c->cfg = *cfg; c->slab = slab; c->geo = make_geometry(*cfg);
+    if (cfg->device >= 0) c->device = cfg->device;
+    else if (cudaGetDevice(&c->device) != cudaSuccess) c->device = 0;
+#define CUC(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { g_last_error = std::string(#call) + " -> " + cudaGetErrorString(_e); ctx_free(c); return MACROC_ERR_CUDA; } } while (0)
+    CUC(cudaSetDevice(c->device));
+    CUC(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CUC(cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking));
+    for (cudaEvent_t *e : {&c->ev_ready, &c->ev_halo, &c->ev_chk[0], &c->ev_chk[1]}) CUC(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+    CUC(cudaEventCreate(&c->ev_t0)); CUC(cudaEventCreate(&c->ev_t1));
+
+    GridDev &g = c->g;
+    g.NX = slab.NX; g.NY = slab.NY; g.NZ = slab.NZ; g.zs = slab.zs; g.nzl = slab.nzl;
+    g.npl = slab.npl; g.nloc = slab.nloc;
+    g.G = (int)(((slab.npl + slab.NX + 1 + 31) / 32) * 32);
+    g.ntiles = (slab.nloc + TILE_NODES - 1) / TILE_NODES;
+    g.S = g.ntiles * TILE_NODES + 2 * (int64_t)g.G + 32;
+
+    for (int i = 0; i < V_COUNT; ++i) {
+        CUC(cudaMalloc(&c->vec[i], sizeof(double) * 3 * g.S));
+        CUC(cudaMemsetAsync(c->vec[i], 0, sizeof(double) * 3 * g.S, c->stream));
+    }
+    CUC(cudaMalloc(&c->Ke, sizeof(double) * 576));
+    CUC(cudaMalloc(&c->T, sizeof(double) * 27 * 243));
+    CUC(cudaMalloc(&c->sums, sizeof(double) * 4));
+    CUC(cudaMalloc(&c->sc, sizeof(CgScalars)));
+    CUC(cudaMallocHost(&c->sums_host, sizeof(double) * 4));
+    CUC(cudaMallocHost(&c->sc_host, sizeof(CgScalars) * 2));
+    CUC(cudaMalloc(&c->stage, sizeof(double) * 3 * (size_t)g.nloc));
+    c->vec_blocks = std::min<int64_t>(cdiv64(g.nloc, 256), 148 * 8);
+    c->spmv_blocks = std::min<int64_t>(cdiv64(g.ntiles, 8), 148 * 8);
+    c->partial_cap = std::max<int64_t>({(int64_t)cdiv64(g.nloc, 128), (int64_t)2 * c->vec_blocks, (int64_t)3 * c->spmv_blocks + 8, (int64_t)4096});
+    CUC(cudaMalloc(&c->partial, sizeof(double) * c->partial_cap));
+
+    // Dirichlet bookkeeping: the reference's lists (bc_init) -> per-node dof mask
+    // over the padded slab (ghost planes included) + owned (index, coef) pairs.
+    {
+        std::vector<int32_t> ix; std::vector<double> cf;
+        build_bc_lists(*cfg, slab, ix, cf);
+        std::vector<uint8_t> mask((size_t)g.S, 0);
+        std::vector<int64_t> own_idx; std::vector<double> own_coef;
+        const int64_t first = (int64_t)slab.zs * slab.npl, last = first + slab.nloc;
+        for (size_t q = 0; q < ix.size(); ++q) {
+            if (ix[q] < 0) continue;
+            int64_t node = ix[q] / 3; int d = ix[q] % 3;
+            int64_t pos = g.G + (node - first);              // may fall in a ghost plane
+            if (pos < 0 || pos >= g.S) continue;
+            mask[(size_t)pos] |= (uint8_t)(1u << d);
+            if (node >= first && node < last) { own_idx.push_back(d * g.S + pos); own_coef.push_back(cf[q]); }
+        }
+        c->nbc = (int)own_idx.size();
+        CUC(cudaMalloc(&c->nodemask, (size_t)g.S));
+        CUC(cudaMemcpyAsync(c->nodemask, mask.data(), (size_t)g.S, cudaMemcpyHostToDevice, c->stream));
+        if (c->nbc) {
+            CUC(cudaMalloc(&c->bc_idx, sizeof(int64_t) * c->nbc));
+            CUC(cudaMalloc(&c->bc_coef, sizeof(double) * c->nbc));
+            CUC(cudaMemcpyAsync(c->bc_idx, own_idx.data(), sizeof(int64_t) * c->nbc, cudaMemcpyHostToDevice, c->stream));
+            CUC(cudaMemcpyAsync(c->bc_coef, own_coef.data(), sizeof(double) * c->nbc, cudaMemcpyHostToDevice, c->stream));
+        }
+        CUC(cudaStreamSynchronize(c->stream));
+    }
+    // element constants: dsh table, D, Ke, class stencils
+    {
+        double D[36];
+        if (cfg->use_D) memcpy(D, cfg->D, sizeof(D)); else isotropic_D(cfg->E, cfg->nu, D);
+        CUC(cudaMemcpyToSymbolAsync(c_D, D, sizeof(D), 0, cudaMemcpyHostToDevice, c->stream));
+        double *dsh_tmp = nullptr;
+        CUC(cudaMalloc(&dsh_tmp, sizeof(double) * 192));
+        LAUNCH(c, k_make_dsh, 1, 64, dsh_tmp);
+        CUC(cudaMemcpyToSymbolAsync(c_dsh, dsh_tmp, sizeof(double) * 192, 0, cudaMemcpyDeviceToDevice, c->stream));
+        LAUNCH(c, k_element_matrix, 3, 192, c->geo.wg, c->Ke);
+        LAUNCH(c, k_stencil_table, cdiv64(27 * 243, 256), 256, c->Ke, c->T);
+        CUC(cudaStreamSynchronize(c->stream));
+        cudaFree(dsh_tmp);
+        CUC(cudaGetLastError());
+    }
+    if (nranks > 1) {
+        ncclUniqueId id;
+        memcpy(&id, id128, 128);
+        ncclResult_t e = ncclCommInitRank(&c->comm, nranks, id, rank);
+        if (e != ncclSuccess) { g_last_error = std::string("ncclCommInitRank -> ") + ncclGetErrorString(e); ctx_free(c); return MACROC_ERR_NCCL; }
+    }
+#undef CUC
+    *out = c;
+    return MACROC_OK;
+}
+
+// ---------------------------------------------------------------------------
+// halo + reductions
+// ---------------------------------------------------------------------------
+
+// DMGlobalToLocal (assembly.c:40-41 and inside every MatMult): one node plane
+// per side and component over NCCL send/recv.
+static int halo_exchange(macroc_ctx *c, double *v, cudaStream_t st)
+{
+    if (!c->comm) return MACROC_OK;
+    const GridDev &g = c->g;
+    const Slab &s = c->slab;
+    NC(c, ncclGroupStart());
+    for (int d = 0; d < 3; ++d) {
+        double *base = v + d * g.S + g.G;
+        if (s.has_lower()) {
+            NC(c, ncclSend(base, (size_t)g.npl, ncclDouble, s.rank - 1, c->comm, st));
+            NC(c, ncclRecv(base - g.npl, (size_t)g.npl, ncclDouble, s.rank - 1, c->comm, st));
+        }
+        if (s.has_upper()) {
+            NC(c, ncclSend(base + g.nloc - g.npl, (size_t)g.npl, ncclDouble, s.rank + 1, c->comm, st));
+            NC(c, ncclRecv(base + g.nloc, (size_t)g.npl, ncclDouble, s.rank + 1, c->comm, st));
+        }
+    }
+    NC(c, ncclGroupEnd());
+    return MACROC_OK;
+}
+
+static int allreduce_sums(macroc_ctx *c, int n)
+{
+    if (!c->comm) return MACROC_OK;
+    NC(c, ncclAllReduce(c->sums, c->sums, (size_t)n, ncclDouble, ncclSum, c->comm, c->stream));
+    return MACROC_OK;
+}
+
+// ---------------------------------------------------------------------------
+// hot path
+// ---------------------------------------------------------------------------
+
+extern "C" double macroc_get_displacement(const macroc_ctx *ctx, int time_s)
+{
+    // bcs.c:52-58 (intended value; the reference function lacks its return)
+    double time = time_s * ctx->cfg.dt;
+    return -1.0 * (time / ctx->cfg.final_time);
+}
+
+extern "C" int macroc_apply_bc_on_u(macroc_ctx *c, double U)
+{
+    if (!c) return MACROC_ERR_ARG;
+    CU(c, cudaSetDevice(c->device));
+    if (c->nbc) LAUNCH(c, k_scatter_bc, cdiv64(c->nbc, 256), 256, c->bc_idx, c->bc_coef, c->nbc, U, c->vec[V_U]);
+    CU(c, cudaGetLastError());
+    return MACROC_OK;
+}
+
+extern "C" int macroc_set_strains(macroc_ctx *c, int materialize)
+{
+    if (!c) return MACROC_ERR_ARG;
+    CU(c, cudaSetDevice(c->device));
+    int rc = halo_exchange(c, c->vec[V_U], c->stream);
+    if (rc) return rc;
+    if (materialize) {
+        const Slab &s = c->slab;
+        int64_t ne = (int64_t)s.nex * s.ney * s.nez;
+        if (!c->strain && ne > 0) {
+            CU(c, cudaMalloc(&c->strain, sizeof(double) * 48 * (size_t)ne));
+            CU(c, cudaMalloc(&c->stress, sizeof(double) * 48 * (size_t)ne));
+        }
+        if (ne > 0) LAUNCH(c, k_strain_stress, cdiv64(ne, 128), 128, c->g, s.ezs, s.nez, c->vec[V_U], c->strain, c->stress);
+        CU(c, cudaGetLastError());
+    }
+    return MACROC_OK;
+}
+
+extern "C" int macroc_assembly_res(macroc_ctx *c, double *norm)
+{
+    if (!c) return MACROC_ERR_ARG;
+    CU(c, cudaSetDevice(c->device));
+    int nblk = cdiv64(c->g.nloc, 128);
+    LAUNCH(c, k_residual, nblk, 128, c->g, c->geo.wg, c->vec[V_U], c->nodemask, c->vec[V_B], c->partial);
+    LAUNCH(c, k_reduce, 1, 256, c->partial, nblk, c->sums);
+    int rc = allreduce_sums(c, 1);
+    if (rc) return rc;
+    CU(c, cudaMemcpyAsync(c->sums_host, c->sums, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    if (norm) *norm = sqrt(c->sums_host[0]);           // VecNorm(b, NORM_2) main.c:67
+    return MACROC_OK;
+}
+
+static int ensure_operator_storage(macroc_ctx *c)
+{
+    if (c->A) return MACROC_OK;
+    size_t bytes = sizeof(double) * (size_t)TILE_DOUBLES * (size_t)c->g.ntiles;
+    cudaError_t e = cudaMalloc(&c->A, bytes);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        FAIL(c, MACROC_ERR_MEM, "operator needs %.2f GB of device memory: %s", bytes / 1e9, cudaGetErrorString(e));
+    }
+    return MACROC_OK;
+}
+
+extern "C" int macroc_assembly_jac(macroc_ctx *c)
+{
+    if (!c) return MACROC_ERR_ARG;
+    CU(c, cudaSetDevice(c->device));
+    if (c->cfg.op == MACROC_OP_MATRIX_FREE) {
+        LAUNCH(c, k_mf_diag, cdiv64(c->g.nloc, 256), 256, c->g, c->T, c->nodemask, c->vec[V_DINV]);
+        c->mf_ready = true;
+    } else {
+        int rc = ensure_operator_storage(c);
+        if (rc) return rc;
+        LAUNCH(c, k_fill_operator, cdiv64(c->g.ntiles, 8), 256, c->g, c->T, c->nodemask, c->A, c->vec[V_DINV]);
+        c->A_valid = true;
+    }
+    CU(c, cudaGetLastError());
+    return MACROC_OK;
+}
+
+// w = A p on the context's stream; p's halo is exchanged on comm_stream while
+// the rows that do not touch a ghost plane are computed.
+static int apply_operator(macroc_ctx *c, int op, double *p, double *w, bool with_dot, const int *done)
+{
+    const GridDev &g = c->g;
+    const bool comm = c->comm != nullptr;
+    const bool mf = op == MACROC_OP_MATRIX_FREE;
+    int64_t lo_end = 0, hi_begin = mf ? g.nloc : g.ntiles;     // interior range in nodes (mf) or tiles
+    if (comm && g.nzl >= 3) {
+        if (mf) { lo_end = g.npl; hi_begin = g.nloc - g.npl; }
+        else { lo_end = (g.npl + TILE_NODES - 1) / TILE_NODES; hi_begin = (g.nloc - g.npl) / TILE_NODES; }
+        if (hi_begin <= lo_end) { lo_end = 0; hi_begin = mf ? g.nloc : g.ntiles; }
+    }
+    const bool split = comm && lo_end > 0;
+    if (comm) {
+        CU(c, cudaEventRecord(c->ev_ready, c->stream));
+        if (split) {
+            CU(c, cudaStreamWaitEvent(c->comm_stream, c->ev_ready, 0));
+            int rc = halo_exchange(c, p, c->comm_stream);
+            if (rc) return rc;
+            CU(c, cudaEventRecord(c->ev_halo, c->comm_stream));
+        } else {
+            int rc = halo_exchange(c, p, c->stream);
+            if (rc) return rc;
+        }
+    }
+    int nparts = 0;
+    auto run = [&](int64_t first, int64_t count) {
+        if (count <= 0) return;
+        int blocks;
+        if (mf) {
+            blocks = (int)std::min<int64_t>(cdiv64(count, 256), 148 * 8);
+            if (with_dot) LAUNCH(c, k_apply_mf<true>, blocks, 256, g, c->T, c->nodemask, p, w, first, count, c->partial + nparts, done);
+            else LAUNCH(c, k_apply_mf<false>, blocks, 256, g, c->T, c->nodemask, p, w, first, count, c->partial + nparts, done);
+        } else {
+            blocks = (int)std::min<int64_t>(cdiv64(count, 8), 148 * 8);
+            if (with_dot) LAUNCH(c, k_spmv<true>, blocks, 256, g, c->A, p, w, first, count, c->partial + nparts, done);
+            else LAUNCH(c, k_spmv<false>, blocks, 256, g, c->A, p, w, first, count, c->partial + nparts, done);
+        }
+        nparts += blocks;
+    };
+    const int64_t total = mf ? g.nloc : g.ntiles;
+    if (split) {
+        run(lo_end, hi_begin - lo_end);
+        CU(c, cudaStreamWaitEvent(c->stream, c->ev_halo, 0));
+        run(0, lo_end);
+        run(hi_begin, total - hi_begin);
+    } else
+        run(0, total);
+    if (with_dot) LAUNCH(c, k_reduce, 1, 256, c->partial, nparts, c->sums);
+    CU(c, cudaGetLastError());
+    return MACROC_OK;
+}
+
+static int cg_iteration(macroc_ctx *c, int op)
+{
+    const GridDev &g = c->g;
+    const int nb = c->vec_blocks;
+    LAUNCH(c, k_cg_update_p, nb, 256, g, c->sc, c->vec[V_R], c->vec[V_DINV], c->vec[V_P]);
+    int rc = apply_operator(c, op, c->vec[V_P], c->vec[V_W], true, &c->sc->done);
+    if (rc) return rc;
+    rc = allreduce_sums(c, 1);
+    if (rc) return rc;
+    LAUNCH(c, k_cg_scalars_pw, 1, 1, c->sc, c->sums);
+    LAUNCH(c, k_cg_update_xr, nb, 256, g, c->sc, c->vec[V_P], c->vec[V_W], c->vec[V_DINV], c->vec[V_DU], c->vec[V_R], c->partial, nb);
+    LAUNCH(c, k_reduce2, 1, 256, c->partial, nb, c->sums);
+    rc = allreduce_sums(c, 2);
+    if (rc) return rc;
+    LAUNCH(c, k_cg_scalars_iter, 1, 1, c->sc, c->sums);
+    return MACROC_OK;
+}
+
+static int cg_begin(macroc_ctx *c, double rtol, double abstol, double dtol, int maxits)
+{
+    const GridDev &g = c->g;
+    const int nb = c->vec_blocks;
+    CgScalars h;
+    memset(&h, 0, sizeof(h));
+    h.rtol = rtol; h.abstol = abstol; h.dtol = dtol; h.maxits = maxits;
+    c->sc_host[0] = h;
+    CU(c, cudaMemcpyAsync(c->sc, &c->sc_host[0], sizeof(CgScalars), cudaMemcpyHostToDevice, c->stream));
+    LAUNCH(c, k_cg_init, nb, 256, g, c->vec[V_B], c->vec[V_DINV], c->vec[V_DU], c->vec[V_R], c->partial, nb);
+    LAUNCH(c, k_reduce2, 1, 256, c->partial, nb, c->sums);
+    int rc = allreduce_sums(c, 2);
+    if (rc) return rc;
+    LAUNCH(c, k_cg_scalars_init, 1, 1, c->sc, c->sums);
+    return MACROC_OK;
+}
+
+extern "C" int macroc_solve_Ax(macroc_ctx *c, int *its, double *rnorm)
+{
+    if (!c) return MACROC_ERR_ARG;
+    CU(c, cudaSetDevice(c->device));
+    const int op = c->cfg.op;
+    if (op == MACROC_OP_ASSEMBLED && !c->A_valid) FAIL(c, MACROC_ERR_ARG, "solve_Ax: assembly_jac has not been called");
+    if (op == MACROC_OP_MATRIX_FREE && !c->mf_ready) FAIL(c, MACROC_ERR_ARG, "solve_Ax: assembly_jac has not been called");
+    int rc = cg_begin(c, c->cfg.ksp_rtol, c->cfg.ksp_abstol, c->cfg.ksp_dtol, c->cfg.ksp_maxits);
+    if (rc) return rc;
+    // The iteration count lives on the device; the host only polls a "done"
+    // flag every `check` iterations (one check behind), kernels launched after
+    // convergence are no-ops, so the count is exactly KSPCG's.
+    const int check = 8;
+    int pending = -1, slot = 0;
+    bool finished = false;
+    for (int it = 0; it < c->cfg.ksp_maxits + 1 && !finished; ++it) {
+        rc = cg_iteration(c, op);
+        if (rc) return rc;
+        if ((it + 1) % check == 0) {
+            CU(c, cudaMemcpyAsync(&c->sc_host[slot], c->sc, sizeof(CgScalars), cudaMemcpyDeviceToHost, c->stream));
+            CU(c, cudaEventRecord(c->ev_chk[slot], c->stream));
+            if (pending >= 0) {
+                CU(c, cudaEventSynchronize(c->ev_chk[pending]));
+                if (c->sc_host[pending].done) finished = true;
+            }
+            pending = slot;
+            slot ^= 1;
+        }
+    }
+    CU(c, cudaMemcpyAsync(&c->sc_host[0], c->sc, sizeof(CgScalars), cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    if (its) *its = c->sc_host[0].its;
+    if (rnorm) *rnorm = c->sc_host[0].dp;       // KSPGetResidualNorm: last preconditioned norm
+    c->ksp_reason = c->sc_host[0].reason;
+    return MACROC_OK;
+}
+
+extern "C" int macroc_ksp_reason(const macroc_ctx *c, int *reason)
+{
+    if (!c || !reason) return MACROC_ERR_ARG;
+    *reason = c->ksp_reason;
+    return MACROC_OK;
+}
+
+extern "C" int macroc_update_u(macroc_ctx *c)
+{
+    if (!c) return MACROC_ERR_ARG;
+    CU(c, cudaSetDevice(c->device));
+    dim3 grid(cdiv64(c->g.nloc, 256), 3);
+    LAUNCH(c, k_axpy1, grid, 256, c->g, c->vec[V_U], c->vec[V_DU]);
+    CU(c, cudaGetLastError());
+    return MACROC_OK;
+}
+
+extern "C" int macroc_calc_force(macroc_ctx *c, double *force)
+{
+    if (!c || !force) return MACROC_ERR_ARG;
+    CU(c, cudaSetDevice(c->device));
+    const Slab &s = c->slab;
+    int64_t count = c->cfg.bc_type == MACROC_BC_BENDING ? (int64_t)s.ney * s.nez : (int64_t)s.nex * s.nez;
+    double local = 0.;
+    if (count > 0) {
+        int nblk = cdiv64(count, 128);
+        LAUNCH(c, k_force, nblk, 128, c->g, s.ezs, s.nez, c->cfg.bc_type, c->geo.dx, c->geo.dy, c->geo.dz, c->cfg.lx,
+               c->cfg.lz, c->geo.rad, c->vec[V_U], c->partial);
+        LAUNCH(c, k_reduce, 1, 256, c->partial, nblk, c->sums);
+    } else
+        CU(c, cudaMemsetAsync(c->sums, 0, sizeof(double), c->stream));
+    int rc = allreduce_sums(c, 1);               // MPI_Reduce(SUM) forces.c:47 (every rank gets it)
+    if (rc) return rc;
+    CU(c, cudaMemcpyAsync(c->sums_host, c->sums, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    local = c->sums_host[0];
+    *force = local;
+    return MACROC_OK;
+}
+
+extern "C" int macroc_time_step(macroc_ctx *c, int time_s, int *newton_its, double *res_norms, int *n_res,
+                                int *ksp_its, double *ksp_rnorms)
+{
+    if (!c) return MACROC_ERR_ARG;
+    // main.c:53-82
+    double U = macroc_get_displacement(c, time_s);
+    int rc = macroc_apply_bc_on_u(c, U);
+    if (rc) return rc;
+    int newton_it = 0, nres = 0;
+    double norm = 0., norm_0 = 0.;
+    while (newton_it < c->cfg.newton_max_its) {
+        if ((rc = macroc_set_strains(c, 0))) return rc;
+        if ((rc = macroc_assembly_res(c, &norm))) return rc;
+        if (res_norms) res_norms[nres] = norm;
+        nres++;
+        if (newton_it == 0) norm_0 = norm;
+        if (norm < c->cfg.newton_min_tol || norm < norm_0 * c->cfg.newton_rel_tol) break;
+        if ((rc = macroc_assembly_jac(c))) return rc;
+        int its = 0; double rn = 0.;
+        if ((rc = macroc_solve_Ax(c, &its, &rn))) return rc;
+        if (ksp_its) ksp_its[newton_it] = its;
+        if (ksp_rnorms) ksp_rnorms[newton_it] = rn;
+        if ((rc = macroc_update_u(c))) return rc;
+        newton_it++;
+    }
+    if (newton_its) *newton_its = newton_it;
+    if (n_res) *n_res = nres;
+    return MACROC_OK;
+}
+
+// ---------------------------------------------------------------------------
+// boundary copies
+// ---------------------------------------------------------------------------
+
+extern "C" int64_t macroc_local_ndof(const macroc_ctx *c) { return c ? 3 * c->g.nloc : 0; }
+extern "C" int64_t macroc_global_ndof(const macroc_ctx *c) { return c ? 3 * (int64_t)c->g.NX * c->g.NY * c->g.NZ : 0; }
+
+static double *which_vec(macroc_ctx *c, int which)
+{
+    switch (which) {
+        case MACROC_VEC_U: return c->vec[V_U];
+        case MACROC_VEC_DU: return c->vec[V_DU];
+        case MACROC_VEC_B: return c->vec[V_B];
+        default: return nullptr;
+    }
+}
+
+extern "C" int macroc_set_vec(macroc_ctx *c, int which, const double *host)
+{
+    if (!c || !host) return MACROC_ERR_ARG;
+    double *v = which_vec(c, which);
+    if (!v) FAIL(c, MACROC_ERR_ARG, "set_vec: unknown vector %d", which);
+    CU(c, cudaSetDevice(c->device));
+    int64_t n = 3 * c->g.nloc;
+    CU(c, cudaMemcpyAsync(c->stage, host, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+    LAUNCH(c, k_aos_to_soa, cdiv64(n, 256), 256, c->g, c->stage, v);
+    CU(c, cudaStreamSynchronize(c->stream));
+    return MACROC_OK;
+}
+
+extern "C" int macroc_get_vec(macroc_ctx *c, int which, double *host)
+{
+    if (!c || !host) return MACROC_ERR_ARG;
+    double *v = which_vec(c, which);
+    if (!v) FAIL(c, MACROC_ERR_ARG, "get_vec: unknown vector %d", which);
+    CU(c, cudaSetDevice(c->device));
+    int64_t n = 3 * c->g.nloc;
+    LAUNCH(c, k_soa_to_aos, cdiv64(n, 256), 256, c->g, v, c->stage);
+    CU(c, cudaMemcpyAsync(host, c->stage, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    return MACROC_OK;
+}
+
+extern "C" int macroc_get_matrix_blocks(macroc_ctx *c, double *host)
+{
+    if (!c || !host) return MACROC_ERR_ARG;
+    if (!c->A_valid) FAIL(c, MACROC_ERR_ARG, "get_matrix_blocks: no assembled operator");
+    CU(c, cudaSetDevice(c->device));
+    const int64_t chunk = 1 << 16;                 // nodes per export chunk
+    double *tmp = nullptr;
+    CU(c, cudaMalloc(&tmp, sizeof(double) * 243 * chunk));
+    for (int64_t n0 = 0; n0 < c->g.nloc; n0 += chunk) {
+        int64_t nn = std::min<int64_t>(chunk, c->g.nloc - n0);
+        LAUNCH(c, k_export_blocks, cdiv64(nn * 243, 256), 256, c->g, reinterpret_cast<const double *>(c->A), n0, nn, tmp);
+        cudaError_t e = cudaMemcpyAsync(host + n0 * 243, tmp, sizeof(double) * 243 * nn, cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) { cudaFree(tmp); FAIL(c, MACROC_ERR_CUDA, "get_matrix_blocks: %s", cudaGetErrorString(e)); }
+    }
+    cudaFree(tmp);
+    return MACROC_OK;
+}
+
+extern "C" int macroc_matmult(macroc_ctx *c, int op, const double *x_host, double *y_host)
+{
+    if (!c || !x_host || !y_host) return MACROC_ERR_ARG;
+    CU(c, cudaSetDevice(c->device));
+    if (op == MACROC_OP_ASSEMBLED && !c->A_valid) FAIL(c, MACROC_ERR_ARG, "matmult: no assembled operator");
+    int64_t n = 3 * c->g.nloc;
+    CU(c, cudaMemcpyAsync(c->stage, x_host, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+    LAUNCH(c, k_aos_to_soa, cdiv64(n, 256), 256, c->g, c->stage, c->vec[V_P]);
+    int rc = apply_operator(c, op, c->vec[V_P], c->vec[V_W], false, nullptr);
+    if (rc) return rc;
+    LAUNCH(c, k_soa_to_aos, cdiv64(n, 256), 256, c->g, c->vec[V_W], c->stage);
+    CU(c, cudaMemcpyAsync(y_host, c->stage, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    return MACROC_OK;
+}
+
+extern "C" int macroc_get_strain_stress(macroc_ctx *c, double *strain, double *stress, int64_t *n_gp)
+{
+    if (!c) return MACROC_ERR_ARG;
+    CU(c, cudaSetDevice(c->device));
+    int64_t ne = (int64_t)c->slab.nex * c->slab.ney * c->slab.nez;
+    if (n_gp) *n_gp = ne * 8;
+    if ((strain || stress) && !c->strain && ne > 0) FAIL(c, MACROC_ERR_ARG, "get_strain_stress: call set_strains(ctx, 1) first");
+    if (strain && ne > 0) CU(c, cudaMemcpyAsync(strain, c->strain, sizeof(double) * 48 * ne, cudaMemcpyDeviceToHost, c->stream));
+    if (stress && ne > 0) CU(c, cudaMemcpyAsync(stress, c->stress, sizeof(double) * 48 * ne, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    return MACROC_OK;
+}
+
+// ---------------------------------------------------------------------------
+// measurement
+// ---------------------------------------------------------------------------
+
+extern "C" uint64_t macroc_launch_count(const macroc_ctx *c) { return c ? c->launches : 0; }
+
+extern "C" int macroc_device_synchronize(macroc_ctx *c)
+{
+    if (!c) return MACROC_ERR_ARG;
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaStreamSynchronize(c->stream));
+    CU(c, cudaStreamSynchronize(c->comm_stream));
+    return MACROC_OK;
+}
+
+extern "C" int macroc_time_kernel(macroc_ctx *c, int what, int reps, int flush_l2, double *ms_mean)
+{
+    if (!c || !ms_mean || reps <= 0) return MACROC_ERR_ARG;
+    CU(c, cudaSetDevice(c->device));
+    const GridDev &g = c->g;
+    if ((what == 0 || what == 2) && !c->A_valid) FAIL(c, MACROC_ERR_ARG, "time_kernel: assemble first");
+    if (flush_l2 && !c->flush) {
+        c->flush_bytes = (size_t)256 << 20;
+        CU(c, cudaMalloc(&c->flush, c->flush_bytes));
+    }
+    if (what == 0 || what == 1) LAUNCH(c, k_fill_pattern, cdiv64(g.nloc, 256), 256, g, c->nodemask, c->vec[V_P]);
+    if (what == 2 || what == 5) {
+        // a never-converging PCG on a synthetic right-hand side: every iteration does the full work
+        if (what == 5) LAUNCH(c, k_mf_diag, cdiv64(g.nloc, 256), 256, g, c->T, c->nodemask, c->vec[V_DINV]);
+        LAUNCH(c, k_fill_pattern, cdiv64(g.nloc, 256), 256, g, c->nodemask, c->vec[V_B]);
+        int rc = cg_begin(c, 0., 0., 1e300, 1 << 30);
+        if (rc) return rc;
+    }
+    double total = 0.;
+    for (int r = 0; r < reps; ++r) {
+        if (flush_l2) CU(c, cudaMemsetAsync(c->flush, r & 0xff, c->flush_bytes, c->stream));
+        CU(c, cudaEventRecord(c->ev_t0, c->stream));
+        int rc = MACROC_OK;
+        switch (what) {
+            case 0: rc = apply_operator(c, MACROC_OP_ASSEMBLED, c->vec[V_P], c->vec[V_W], true, nullptr); break;
+            case 1: rc = apply_operator(c, MACROC_OP_MATRIX_FREE, c->vec[V_P], c->vec[V_W], true, nullptr); break;
+            case 2: rc = cg_iteration(c, MACROC_OP_ASSEMBLED); break;
+            case 5: rc = cg_iteration(c, MACROC_OP_MATRIX_FREE); break;
+            case 3: {
+                int save = c->cfg.op; c->cfg.op = MACROC_OP_ASSEMBLED;
+                rc = macroc_assembly_jac(c);
+                c->cfg.op = save;
+                break;
+            }
+            case 4: {
+                int nblk = cdiv64(g.nloc, 128);
+                LAUNCH(c, k_residual, nblk, 128, g, c->geo.wg, c->vec[V_U], c->nodemask, c->vec[V_B], c->partial);
+                LAUNCH(c, k_reduce, 1, 256, c->partial, nblk, c->sums);
+                break;
+            }
+            default: FAIL(c, MACROC_ERR_ARG, "time_kernel: unknown kernel %d", what);
+        }
+        if (rc) return rc;
+        CU(c, cudaEventRecord(c->ev_t1, c->stream));
+        CU(c, cudaEventSynchronize(c->ev_t1));
+        float ms = 0.f;
+        CU(c, cudaEventElapsedTime(&ms, c->ev_t0, c->ev_t1));
+        total += ms;
+    }
+    *ms_mean = total / reps;
+    return MACROC_OK;
+}

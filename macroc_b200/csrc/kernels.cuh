@@ -1,0 +1,693 @@
+// kernels.cuh -- fp64 CUDA kernels (sm_100a) for MacroC's macro-scale hot path.
+//
+// Data layout in HBM (per rank / z-slab):
+//   * nodal vectors are SoA by displacement component, v[c*S + G + ln], ln the
+//     owned node in DMDA natural order, G >= NX*NY + NX + 1 nodes of padding on
+//     both sides that also holds the ghost planes (so every 27-point neighbour
+//     is at a uniform linear offset and always in bounds);
+//   * the assembled operator is a fixed 27-slot 3x3-block stencil ("index-free
+//     block-DIA"): tiles of 32 consecutive owned nodes, inside a tile entry
+//     k = slot*9 + 3*r + c of node `lane` sits at double index
+//     ((k>>1)*32 + lane)*2 + (k&1); a tile is one contiguous 62 464-byte chunk
+//     (244 entries per node, entry 243 is padding), read with one coalesced
+//     128-bit load per lane per entry pair.
+#pragma once
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace macroc {
+
+constexpr int TILE_NODES = 32;
+constexpr int ENTRIES = 243;                 // 27 slots x 9
+constexpr int PAIRS = 122;                   // ceil(243/2)
+constexpr int TILE_DOUBLES = PAIRS * 2 * TILE_NODES;   // 7808 doubles = 62 464 B
+
+// Signs of the 8 hex nodes / Gauss points in natural coordinates
+// (reference include/macroc.h:61-69 and the dsh table of assembly.c:200-232).
+__constant__ int c_sgn[8][3] = {{-1, -1, -1}, {+1, -1, -1}, {+1, +1, -1}, {-1, +1, -1},
+                                {-1, -1, +1}, {+1, -1, +1}, {+1, +1, +1}, {-1, +1, +1}};
+// dsh[gp][n][d]: shape-function derivatives of the unit-cube element
+// (assembly.c:198-232), filled once by k_init_dsh and then read-only.
+__constant__ double c_dsh[8][8][3];
+__constant__ double c_D[36];                 // homogenised tangent (row-major 6x6)
+
+struct GridDev {
+    int NX, NY, NZ;          // global grid
+    int zs, nzl;             // owned planes
+    int64_t npl, nloc;       // nodes per plane / owned nodes
+    int64_t S;               // SoA component stride (doubles)
+    int G;                   // padding (nodes) in front of owned node 0
+    int64_t ntiles;
+};
+
+struct CgScalars {
+    double beta, betaold, pw, zz, zr, dp, dp0, ttol, rtol, abstol, dtol;
+    int its, maxits, done, reason;
+};
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Deterministic block reduction (fixed order): returns the block sum in thread 0.
+template <int NW>
+__device__ __forceinline__ double block_sum(double v, double *sm)
+{
+    v = warp_sum(v);
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) sm[w] = v;
+    __syncthreads();
+    double s = 0.;
+    if (threadIdx.x == 0)
+        for (int q = 0; q < NW; ++q) s += sm[q];
+    __syncthreads();
+    return s;
+}
+
+// ---------------------------------------------------------------------------
+// Element constants
+// ---------------------------------------------------------------------------
+
+// calc_B's dsh table (assembly.c:195-232) with explicit round-to-nearest ops so
+// the bits match the CPU evaluation of the same expressions.
+__global__ void k_make_dsh(double *out /* [8][8][3] */)
+{
+    int t = threadIdx.x;
+    if (t >= 64) return;
+    int gp = t >> 3, n = t & 7;
+    const double CONSTXG = 0.577350269189626;
+    double xi = c_sgn[gp][0] * CONSTXG, eta = c_sgn[gp][1] * CONSTXG, zeta = c_sgn[gp][2] * CONSTXG;
+    double fx = __dadd_rn(1., c_sgn[n][0] * xi), fy = __dadd_rn(1., c_sgn[n][1] * eta),
+           fz = __dadd_rn(1., c_sgn[n][2] * zeta);
+    out[(gp * 8 + n) * 3 + 0] = c_sgn[n][0] * __dmul_rn(fy, fz) / 8. * 2.;
+    out[(gp * 8 + n) * 3 + 1] = c_sgn[n][1] * __dmul_rn(fx, fz) / 8. * 2.;
+    out[(gp * 8 + n) * 3 + 2] = c_sgn[n][2] * __dmul_rn(fx, fy) / 8. * 2.;
+}
+
+__device__ __forceinline__ double Bentry(int gp, int row, int col)
+{
+    // B[row][3n+d] of assembly.c:234-253
+    int n = col / 3, d = col % 3;
+    const double *h = c_dsh[gp][n];
+    switch (row) {
+        case 0: return d == 0 ? h[0] : 0.;
+        case 1: return d == 1 ? h[1] : 0.;
+        case 2: return d == 2 ? h[2] : 0.;
+        case 3: return d == 0 ? h[1] : (d == 1 ? h[0] : 0.);
+        case 4: return d == 0 ? h[2] : (d == 2 ? h[0] : 0.);
+        default: return d == 1 ? h[2] : (d == 2 ? h[1] : 0.);
+    }
+}
+
+// Ke = sum_gp B^T C B wg for a tangent that is the same at the 8 Gauss points
+// (assembly.c:87-101).  One thread per entry, the reference's summation order
+// (gp, k, l) and rounding (no FMA contraction) -> bitwise the CPU value.
+__global__ void k_element_matrix(double wg, double *Ke /* [24][24] */)
+{
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 576) return;
+    int i = t / 24, j = t % 24;
+    double acc = 0.;
+    for (int gp = 0; gp < 8; ++gp)
+        for (int k = 0; k < 6; ++k) {
+            double bki = Bentry(gp, k, i);
+            for (int l = 0; l < 6; ++l) {
+                double term = __dmul_rn(__dmul_rn(__dmul_rn(bki, c_D[k * 6 + l]), Bentry(gp, l, j)), wg);
+                acc = __dadd_rn(acc, term);
+            }
+        }
+    Ke[t] = acc;
+}
+
+__device__ __host__ __forceinline__ int local_node_of_pos(int px, int py, int pz)
+{
+    return (py ? (px ? 2 : 3) : (px ? 1 : 0)) + 4 * pz;
+}
+// position (0/1 per axis) of local node n inside its element (same table as c_sgn)
+__device__ __host__ __forceinline__ constexpr int node_px(int n) { return ((n & 3) == 1 || (n & 3) == 2) ? 1 : 0; }
+__device__ __host__ __forceinline__ constexpr int node_py(int n) { return (n & 3) >= 2 ? 1 : 0; }
+__device__ __host__ __forceinline__ constexpr int node_pz(int n) { return n >> 2; }
+
+// Pre-summed 27-slot stencils for the 27 node classes (lower face / interior /
+// upper face per axis): T[type][slot][3][3] = sum over the elements that exist
+// around a node of that class, in increasing element order (the order
+// MatSetValuesLocal(ADD_VALUES) accumulates them, assembly.c:85-108).
+__global__ void k_stencil_table(const double *__restrict__ Ke, double *__restrict__ T /* [27][27][9] */)
+{
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 27 * 27 * 9) return;
+    int cc = t % 3, rr = (t / 3) % 3, slot = (t / 9) % 27, type = t / 243;
+    int tx = type % 3, ty = (type / 3) % 3, tz = type / 9;
+    int ddx = slot % 3 - 1, ddy = (slot / 3) % 3 - 1, ddz = slot / 9 - 1;
+    double acc = 0.;
+    for (int oz = -1; oz <= 0; ++oz)
+        for (int oy = -1; oy <= 0; ++oy)
+            for (int ox = -1; ox <= 0; ++ox) {
+                // element with origin node + o exists?
+                if ((ox == -1 && tx == 0) || (ox == 0 && tx == 2)) continue;
+                if ((oy == -1 && ty == 0) || (oy == 0 && ty == 2)) continue;
+                if ((oz == -1 && tz == 0) || (oz == 0 && tz == 2)) continue;
+                int bx = ddx - ox, by = ddy - oy, bz = ddz - oz;   // neighbour's position in the element
+                if (bx < 0 || bx > 1 || by < 0 || by > 1 || bz < 0 || bz > 1) continue;
+                int a = local_node_of_pos(-ox, -oy, -oz), b = local_node_of_pos(bx, by, bz);
+                acc = __dadd_rn(acc, Ke[(a * 3 + rr) * 24 + b * 3 + cc]);
+            }
+    T[t] = acc;
+}
+
+__device__ __forceinline__ int node_class(int c, int N) { return c == 0 ? 0 : (c == N - 1 ? 2 : 1); }
+
+// ---------------------------------------------------------------------------
+// Jacobian "assembly" for a tangent that is uniform over the grid: expand the
+// class stencils into the tile-blocked operator and apply MatZeroRowsColumns
+// (A <- M A M + (I-M), bcs.c:341-347) on the fly.  Pure HBM-write bound:
+// 1 952 B per node.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_fill_operator(GridDev g, const double *__restrict__ T, const uint8_t *__restrict__ nodemask,
+                double2 *__restrict__ A, double *__restrict__ dinv)
+{
+    int64_t tile = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (tile >= g.ntiles) return;
+    int lane = threadIdx.x & 31;
+    int64_t ln = tile * TILE_NODES + lane;
+    bool valid = ln < g.nloc;
+    int i = 0, j = 0, k = 0, type = 13;
+    unsigned own = 0;
+    if (valid) {
+        i = (int)(ln % g.NX);
+        j = (int)((ln / g.NX) % g.NY);
+        k = (int)(ln / g.npl) + g.zs;
+        type = node_class(i, g.NX) + 3 * node_class(j, g.NY) + 9 * node_class(k, g.NZ);
+        own = nodemask[g.G + ln];
+    }
+    const double *Tt = T + type * 243;
+    double2 *At = A + tile * (PAIRS * TILE_NODES) + lane;
+    double carry = 0.;
+    double diag[3] = {1., 1., 1.};
+#pragma unroll
+    for (int kk = 0; kk < 244; ++kk) {
+        double v = 0.;
+        if (kk < ENTRIES) {
+            const int slot = kk / 9, rr = (kk % 9) / 3, cc = kk % 3;
+            const int ddx = slot % 3 - 1, ddy = (slot / 3) % 3 - 1, ddz = slot / 9 - 1;
+            if (valid) {
+                v = __ldg(Tt + kk);
+                unsigned nb = nodemask[g.G + ln + ddx + (int64_t)g.NX * ddy + g.npl * ddz];
+                if (((own >> rr) & 1u) || ((nb >> cc) & 1u)) v = (slot == 13 && rr == cc) ? 1. : 0.;
+                if (slot == 13 && rr == cc) diag[rr] = v;
+            }
+        }
+        if (kk & 1) At[(kk >> 1) * TILE_NODES] = make_double2(carry, v);
+        else carry = v;
+    }
+    if (valid) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) dinv[d * g.S + g.G + ln] = diag[d] != 0. ? 1. / diag[d] : 1.;   // PCJACOBI
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Assembled block-stencil SpMV  w = A p  (+ fused partial of p.w)
+// HBM bound: 1 952 B of operator per node against 48 B of vectors.
+// ---------------------------------------------------------------------------
+template <bool DOT>
+__global__ void __launch_bounds__(256)
+k_spmv(GridDev g, const double2 *__restrict__ A, const double *__restrict__ p, double *__restrict__ w,
+       int64_t tile0, int64_t ntiles, double *__restrict__ partial, const int *__restrict__ done)
+{
+    __shared__ double sm[8];
+    if (done && *done) return;
+    const int lane = threadIdx.x & 31;
+    const int64_t wstride = (int64_t)gridDim.x * (blockDim.x >> 5);
+    const int64_t NX = g.NX, npl = g.npl;
+    double dot = 0.;
+    for (int64_t tile = tile0 + (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+         tile < tile0 + ntiles; tile += wstride) {
+        int64_t ln = tile * TILE_NODES + lane;
+        const double2 *At = A + tile * (PAIRS * TILE_NODES) + lane;
+        const double *p0 = p + g.G + ln, *p1 = p0 + g.S, *p2 = p1 + g.S;
+        double a0 = 0., a1 = 0., a2 = 0., pc0 = 0., pc1 = 0., pc2 = 0.;
+        // two slots (18 entries = 9 pairs) per step; slot 26 + padding at the end
+#pragma unroll
+        for (int gq = 0; gq < 13; ++gq) {
+            double2 v[9];
+#pragma unroll
+            for (int q = 0; q < 9; ++q) v[q] = __ldcs(At + (gq * 9 + q) * TILE_NODES);
+            const double *e = reinterpret_cast<const double *>(v);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int slot = 2 * gq + h;
+                const int ddx = slot % 3 - 1, ddy = (slot / 3) % 3 - 1, ddz = slot / 9 - 1;
+                const int64_t off = ddx + NX * ddy + npl * ddz;
+                double x0 = __ldg(p0 + off), x1 = __ldg(p1 + off), x2 = __ldg(p2 + off);
+                if (slot == 13) { pc0 = x0; pc1 = x1; pc2 = x2; }
+                const double *m = e + 9 * h;
+                a0 = fma(m[0], x0, a0); a0 = fma(m[1], x1, a0); a0 = fma(m[2], x2, a0);
+                a1 = fma(m[3], x0, a1); a1 = fma(m[4], x1, a1); a1 = fma(m[5], x2, a1);
+                a2 = fma(m[6], x0, a2); a2 = fma(m[7], x1, a2); a2 = fma(m[8], x2, a2);
+            }
+        }
+        {
+            double2 v[5];
+#pragma unroll
+            for (int q = 0; q < 5; ++q) v[q] = __ldcs(At + (117 + q) * TILE_NODES);
+            const double *m = reinterpret_cast<const double *>(v);
+            const int64_t off = 1 + NX + npl;    // slot 26 = (+1,+1,+1)
+            double x0 = __ldg(p0 + off), x1 = __ldg(p1 + off), x2 = __ldg(p2 + off);
+            a0 = fma(m[0], x0, a0); a0 = fma(m[1], x1, a0); a0 = fma(m[2], x2, a0);
+            a1 = fma(m[3], x0, a1); a1 = fma(m[4], x1, a1); a1 = fma(m[5], x2, a1);
+            a2 = fma(m[6], x0, a2); a2 = fma(m[7], x1, a2); a2 = fma(m[8], x2, a2);
+        }
+        if (ln < g.nloc) {
+            double *w0 = w + g.G + ln;
+            w0[0] = a0; w0[g.S] = a1; w0[2 * g.S] = a2;
+            dot += a0 * pc0 + a1 * pc1 + a2 * pc2;
+        }
+    }
+    if (DOT) {
+        double s = block_sum<8>(dot, sm);
+        if (threadIdx.x == 0) partial[blockIdx.x] = s;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Matrix-free apply  y = (M K M + I - M) x  with the class stencils
+// (27 x 243 doubles, L1 resident): 16 B/DOF of HBM traffic, FP64-pipe bound.
+// ---------------------------------------------------------------------------
+template <bool DOT>
+__global__ void __launch_bounds__(256)
+k_apply_mf(GridDev g, const double *__restrict__ T, const uint8_t *__restrict__ nodemask,
+           const double *__restrict__ x, double *__restrict__ y, int64_t node0, int64_t nnodes,
+           double *__restrict__ partial, const int *__restrict__ done)
+{
+    __shared__ double sm[8];
+    if (done && *done) return;
+    double dot = 0.;
+    for (int64_t ln = node0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; ln < node0 + nnodes && ln < g.nloc;
+         ln += (int64_t)gridDim.x * blockDim.x) {
+        int i = (int)(ln % g.NX), j = (int)((ln / g.NX) % g.NY), k = (int)(ln / g.npl) + g.zs;
+        int type = node_class(i, g.NX) + 3 * node_class(j, g.NY) + 9 * node_class(k, g.NZ);
+        const double *Tt = T + type * 243;
+        const double *x0p = x + g.G + ln, *x1p = x0p + g.S, *x2p = x1p + g.S;
+        const uint8_t *mk = nodemask + g.G + ln;
+        const int64_t NX = g.NX, npl = g.npl;
+        double a0 = 0., a1 = 0., a2 = 0., xc0 = 0., xc1 = 0., xc2 = 0.;
+#pragma unroll
+        for (int slot = 0; slot < 27; ++slot) {
+            const int ddx = slot % 3 - 1, ddy = (slot / 3) % 3 - 1, ddz = slot / 9 - 1;
+            const int64_t off = ddx + NX * ddy + npl * ddz;
+            unsigned nb = mk[off];
+            double x0 = __ldg(x0p + off), x1 = __ldg(x1p + off), x2 = __ldg(x2p + off);
+            if (slot == 13) { xc0 = x0; xc1 = x1; xc2 = x2; }
+            x0 = (nb & 1u) ? 0. : x0; x1 = (nb & 2u) ? 0. : x1; x2 = (nb & 4u) ? 0. : x2;
+            const double *m = Tt + slot * 9;
+            a0 = fma(__ldg(m + 0), x0, a0); a0 = fma(__ldg(m + 1), x1, a0); a0 = fma(__ldg(m + 2), x2, a0);
+            a1 = fma(__ldg(m + 3), x0, a1); a1 = fma(__ldg(m + 4), x1, a1); a1 = fma(__ldg(m + 5), x2, a1);
+            a2 = fma(__ldg(m + 6), x0, a2); a2 = fma(__ldg(m + 7), x1, a2); a2 = fma(__ldg(m + 8), x2, a2);
+        }
+        unsigned own = mk[0];
+        if (own & 1u) a0 = xc0;
+        if (own & 2u) a1 = xc1;
+        if (own & 4u) a2 = xc2;
+        double *y0 = y + g.G + ln;
+        y0[0] = a0; y0[g.S] = a1; y0[2 * g.S] = a2;
+        dot += a0 * xc0 + a1 * xc1 + a2 * xc2;
+    }
+    if (DOT) {
+        double s = block_sum<8>(dot, sm);
+        if (threadIdx.x == 0) partial[blockIdx.x] = s;
+    }
+}
+
+// Jacobi diagonal for the matrix-free operator (PCJACOBI needs diag(A)).
+__global__ void k_mf_diag(GridDev g, const double *__restrict__ T, const uint8_t *__restrict__ nodemask,
+                          double *__restrict__ dinv)
+{
+    int64_t ln = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ln >= g.nloc) return;
+    int i = (int)(ln % g.NX), j = (int)((ln / g.NX) % g.NY), k = (int)(ln / g.npl) + g.zs;
+    int type = node_class(i, g.NX) + 3 * node_class(j, g.NY) + 9 * node_class(k, g.NZ);
+    unsigned own = nodemask[g.G + ln];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        double v = ((own >> d) & 1u) ? 1. : T[type * 243 + 13 * 9 + d * 4];
+        dinv[d * g.S + g.G + ln] = v != 0. ? 1. / v : 1.;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Residual  b = -(sum_e sum_gp B^T sigma wg), Dirichlet rows -> 0, + |b|^2
+// (set_strains assembly.c:25-66, sigma = D eps, assembly_res :120-176).
+// Gather form: one thread per owned node walks its <= 8 elements in increasing
+// element order (the reference's accumulation order), so no atomics, no
+// colouring and no reverse halo: the element layer above the slab is
+// integrated redundantly from the upper ghost plane of u.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void element_strain(const double (&ue)[8][3], int gp, double (&eps)[6])
+{
+    double e0 = 0., e1 = 0., e2 = 0., e3 = 0., e4 = 0., e5 = 0.;
+#pragma unroll
+    for (int n = 0; n < 8; ++n) {
+        const double hx = c_dsh[gp][n][0], hy = c_dsh[gp][n][1], hz = c_dsh[gp][n][2];
+        e0 = fma(hx, ue[n][0], e0);
+        e1 = fma(hy, ue[n][1], e1);
+        e2 = fma(hz, ue[n][2], e2);
+        e3 = fma(hy, ue[n][0], e3); e3 = fma(hx, ue[n][1], e3);
+        e4 = fma(hz, ue[n][0], e4); e4 = fma(hx, ue[n][2], e4);
+        e5 = fma(hz, ue[n][1], e5); e5 = fma(hy, ue[n][2], e5);
+    }
+    eps[0] = e0; eps[1] = e1; eps[2] = e2; eps[3] = e3; eps[4] = e4; eps[5] = e5;
+}
+
+__device__ __forceinline__ void stress_of(const double (&eps)[6], double (&sig)[6])
+{
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        double t = 0.;
+#pragma unroll
+        for (int j = 0; j < 6; ++j) t = fma(c_D[i * 6 + j], eps[j], t);
+        sig[i] = t;
+    }
+}
+
+__device__ __forceinline__ void gather_element(const double *__restrict__ u, const GridDev &g,
+                                               int64_t base /* SoA index of element origin */,
+                                               double (&ue)[8][3])
+{
+    const int64_t NX = g.NX, npl = g.npl;
+#pragma unroll
+    for (int n = 0; n < 8; ++n) {
+        const int64_t q = base + node_px(n) + NX * node_py(n) + npl * node_pz(n);
+#pragma unroll
+        for (int d = 0; d < 3; ++d) ue[n][d] = __ldg(u + d * g.S + q);
+    }
+}
+
+__global__ void __launch_bounds__(128)
+k_residual(GridDev g, double wg, const double *__restrict__ u, const uint8_t *__restrict__ nodemask,
+           double *__restrict__ b, double *__restrict__ partial)
+{
+    __shared__ double sm[4];
+    int64_t ln = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    double sq = 0.;
+    if (ln < g.nloc) {
+        int i = (int)(ln % g.NX), j = (int)((ln / g.NX) % g.NY), k = (int)(ln / g.npl) + g.zs;
+        double r0 = 0., r1 = 0., r2 = 0.;
+        for (int oz = -1; oz <= 0; ++oz)
+            for (int oy = -1; oy <= 0; ++oy)
+                for (int ox = -1; ox <= 0; ++ox) {
+                    int ei = i + ox, ej = j + oy, ek = k + oz;
+                    if (ei < 0 || ei >= g.NX - 1 || ej < 0 || ej >= g.NY - 1 || ek < 0 || ek >= g.NZ - 1) continue;
+                    int a = local_node_of_pos(-ox, -oy, -oz);
+                    double ue[8][3];
+                    gather_element(u, g, g.G + ln + ox + (int64_t)g.NX * oy + g.npl * oz, ue);
+                    double be0 = 0., be1 = 0., be2 = 0.;
+#pragma unroll
+                    for (int gp = 0; gp < 8; ++gp) {
+                        double eps[6], sig[6];
+                        element_strain(ue, gp, eps);
+                        stress_of(eps, sig);
+                        const double hx = c_dsh[gp][a][0], hy = c_dsh[gp][a][1], hz = c_dsh[gp][a][2];
+                        // be[i] += B[j][i]*stress[j]*wg, j ascending (assembly.c:151-153)
+                        be0 += hx * sig[0] * wg; be0 += hy * sig[3] * wg; be0 += hz * sig[4] * wg;
+                        be1 += hy * sig[1] * wg; be1 += hx * sig[3] * wg; be1 += hz * sig[5] * wg;
+                        be2 += hz * sig[2] * wg; be2 += hx * sig[4] * wg; be2 += hy * sig[5] * wg;
+                    }
+                    r0 += be0; r1 += be1; r2 += be2;
+                }
+        unsigned own = nodemask[g.G + ln];
+        r0 = (own & 1u) ? 0. : -r0;      // apply_bc_on_res (bcs.c:350-362) + VecScale(-1) (:173)
+        r1 = (own & 2u) ? 0. : -r1;
+        r2 = (own & 4u) ? 0. : -r2;
+        double *b0 = b + g.G + ln;
+        b0[0] = r0; b0[g.S] = r1; b0[2 * g.S] = r2;
+        sq = r0 * r0 + r1 * r1 + r2 * r2;
+    }
+    double s = block_sum<4>(sq, sm);
+    if (threadIdx.x == 0) partial[blockIdx.x] = s;
+}
+
+// set_strains with materialisation: strain/stress[gpi*6 + i], gpi = ie*8 + gp
+// (assembly.c:58), ie the rank-local element in DMDAGetElements order.
+__global__ void __launch_bounds__(128)
+k_strain_stress(GridDev g, int ezs, int nez, const double *__restrict__ u, double *__restrict__ strain,
+                double *__restrict__ stress)
+{
+    int64_t ie = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t nex = g.NX - 1, ney = g.NY - 1;
+    if (ie >= nex * ney * nez) return;
+    int ei = (int)(ie % nex), ej = (int)((ie / nex) % ney), ek = (int)(ie / (nex * ney)) + ezs;
+    int64_t base = g.G + ei + (int64_t)g.NX * ej + g.npl * (ek - g.zs);
+    double ue[8][3];
+    gather_element(u, g, base, ue);
+#pragma unroll
+    for (int gp = 0; gp < 8; ++gp) {
+        double eps[6], sig[6];
+        element_strain(ue, gp, eps);
+        stress_of(eps, sig);
+#pragma unroll
+        for (int q = 0; q < 6; ++q) {
+            strain[(ie * 8 + gp) * 6 + q] = eps[q];
+            stress[(ie * 8 + gp) * 6 + q] = sig[q];
+        }
+    }
+}
+
+// forces.c:58-106 / :115-166: sum of the 8 Gauss-point stresses of the elements
+// next to the loaded boundary, component [3]*dy*dz (bending) or [1]*dx*dz (circle).
+__global__ void __launch_bounds__(128)
+k_force(GridDev g, int ezs, int nez, int bc_type, double dx, double dy, double dz, double lx, double lz,
+        double rad, const double *__restrict__ u, double *__restrict__ partial)
+{
+    __shared__ double sm[4];
+    int64_t nex = g.NX - 1, ney = g.NY - 1;
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    double f = 0.;
+    int64_t count = bc_type == 0 ? ney * nez : nex * nez;
+    if (t < count) {
+        int ei, ej, ek;
+        bool take = true;
+        if (bc_type == 0) { ei = (int)nex - 1; ej = (int)(t % ney); ek = (int)(t / ney) + ezs; }
+        else {
+            ei = (int)(t % nex); ej = (int)ney - 1; ek = (int)(t / nex) + ezs;
+            // forces.c:138-141: ghost start + local element index
+            int sk = ezs;
+            double xx = __dsub_rn(lx / 2., __dadd_rn(__dmul_rn((double)ei, dx), dx / 2.));
+            double zz = __dsub_rn(lz / 2., __dadd_rn(__dmul_rn((double)(sk + (ek - ezs)), dz), dz / 2.));
+            take = (__dadd_rn(__dmul_rn(xx, xx), __dmul_rn(zz, zz))) < rad * rad;
+        }
+        if (take) {
+            int64_t base = g.G + ei + (int64_t)g.NX * ej + g.npl * (ek - g.zs);
+            double ue[8][3];
+            gather_element(u, g, base, ue);
+            double ave = 0.;
+            const int comp = bc_type == 0 ? 3 : 1;
+#pragma unroll
+            for (int gp = 0; gp < 8; ++gp) {
+                double eps[6], sig[6];
+                element_strain(ue, gp, eps);
+                stress_of(eps, sig);
+                ave += sig[comp];
+            }
+            f = bc_type == 0 ? ave * dy * dz : ave * dx * dz;
+        }
+    }
+    double s = block_sum<4>(f, sm);
+    if (threadIdx.x == 0) partial[blockIdx.x] = s;
+}
+
+// ---------------------------------------------------------------------------
+// Small vector kernels (owned range only; SoA, blockIdx.y = component)
+// ---------------------------------------------------------------------------
+__global__ void k_scatter_bc(const int64_t *__restrict__ idx, const double *__restrict__ coef, int n, double U,
+                             double *__restrict__ u)
+{
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) u[idx[t]] = coef[t] * U;            // VecSetValues(INSERT) bcs.c:85,140
+}
+
+__global__ void k_axpy1(GridDev g, double *__restrict__ y, const double *__restrict__ x)
+{
+    int64_t ln = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ln >= g.nloc) return;
+    int64_t q = blockIdx.y * g.S + g.G + ln;
+    y[q] += 1. * x[q];                              // VecAXPY(u, 1., du) main.c:79
+}
+
+__global__ void k_aos_to_soa(GridDev g, const double *__restrict__ in, double *__restrict__ out)
+{
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= 3 * g.nloc) return;
+    int64_t ln = e / 3; int d = (int)(e % 3);
+    out[d * g.S + g.G + ln] = in[e];
+}
+
+__global__ void k_soa_to_aos(GridDev g, const double *__restrict__ in, double *__restrict__ out)
+{
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= 3 * g.nloc) return;
+    int64_t ln = e / 3; int d = (int)(e % 3);
+    out[e] = in[d * g.S + g.G + ln];
+}
+
+__global__ void k_export_blocks(GridDev g, const double *__restrict__ A, int64_t node0, int64_t nnodes,
+                                double *__restrict__ out /* [nnodes][243] */)
+{
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nnodes * 243) return;
+    int64_t ln = node0 + e / 243; int kk = (int)(e % 243);
+    int64_t tile = ln / TILE_NODES; int lane = (int)(ln % TILE_NODES);
+    out[e] = A[tile * TILE_DOUBLES + ((int64_t)(kk >> 1) * TILE_NODES + lane) * 2 + (kk & 1)];
+}
+
+// fixed-order reduction of per-block partials: out[0..nout) = sum over blocks
+__global__ void k_reduce(const double *__restrict__ partial, int nblocks, double *__restrict__ out)
+{
+    __shared__ double sm[8];
+    double s = 0.;
+    for (int q = threadIdx.x; q < nblocks; q += blockDim.x) s += partial[q];
+    s = block_sum<8>(s, sm);
+    if (threadIdx.x == 0) out[0] = s;
+}
+
+__global__ void k_fill(double *p, int64_t n, double v)
+{
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < n) p[e] = v;
+}
+
+// deterministic synthetic vector of SURVEY.md 8d: x = sin(0.37*gdof) + 0.1 on free dofs
+__global__ void k_fill_pattern(GridDev g, const uint8_t *__restrict__ nodemask, double *__restrict__ v)
+{
+    int64_t ln = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ln >= g.nloc) return;
+    unsigned own = nodemask[g.G + ln];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        double gd = (double)((ln + (int64_t)g.zs * g.npl) * 3 + d);
+        v[d * g.S + g.G + ln] = ((own >> d) & 1u) ? 0. : sin(0.37 * gd) + 0.1;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// PCG (KSPCG + PCJACOBI, PETSc semantics -- SURVEY.md 8c item 6)
+// ---------------------------------------------------------------------------
+
+// r = b, x = 0, z = r*dinv; partials of z.z and z.r
+__global__ void __launch_bounds__(256)
+k_cg_init(GridDev g, const double *__restrict__ b, const double *__restrict__ dinv, double *__restrict__ x,
+          double *__restrict__ r, double *__restrict__ partial /* [2][nblk] */, int nblk)
+{
+    __shared__ double sm[8];
+    double zz = 0., zr = 0.;
+    for (int64_t ln = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; ln < g.nloc; ln += (int64_t)gridDim.x * blockDim.x) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            int64_t q = d * g.S + g.G + ln;
+            double rv = b[q], z = rv * dinv[q];
+            x[q] = 0.; r[q] = rv;
+            zz = fma(z, z, zz); zr = fma(z, rv, zr);
+        }
+    }
+    double s0 = block_sum<8>(zz, sm), s1 = block_sum<8>(zr, sm);
+    if (threadIdx.x == 0) { partial[blockIdx.x] = s0; partial[nblk + blockIdx.x] = s1; }
+}
+
+// scalar bookkeeping after the initial residual (KSPSolve_CG prologue +
+// KSPConvergedDefault at it 0)
+__global__ void k_cg_scalars_init(CgScalars *s, const double *sums /* zz, zr */)
+{
+    double dp = sqrt(sums[0]);
+    s->dp = s->dp0 = dp;
+    s->ttol = fmax(s->rtol * dp, s->abstol);
+    s->beta = sums[1]; s->betaold = 1.;
+    s->its = 0; s->done = 0; s->reason = 0;
+    if (dp <= s->ttol) { s->done = 1; s->reason = dp <= s->abstol ? 3 : 2; }
+    else if (s->beta == 0.) { s->its = 1; s->done = 1; s->reason = 3; }
+}
+
+// p = z + (beta/betaold) p   (first iteration: p = z), z = r*dinv recomputed
+__global__ void __launch_bounds__(256)
+k_cg_update_p(GridDev g, const CgScalars *__restrict__ s, const double *__restrict__ r,
+              const double *__restrict__ dinv, double *__restrict__ p)
+{
+    if (s->done) return;
+    const bool first = s->its == 0;
+    const double bb = s->beta / s->betaold;
+    for (int64_t ln = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; ln < g.nloc; ln += (int64_t)gridDim.x * blockDim.x) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            int64_t q = d * g.S + g.G + ln;
+            double z = r[q] * dinv[q];
+            p[q] = first ? z : fma(bb, p[q], z);
+        }
+    }
+}
+
+// a = beta/(p.w); x += a p; r -= a w; z = r*dinv; partials z.z, z.r
+__global__ void __launch_bounds__(256)
+k_cg_update_xr(GridDev g, const CgScalars *__restrict__ s, const double *__restrict__ p,
+               const double *__restrict__ w, const double *__restrict__ dinv, double *__restrict__ x,
+               double *__restrict__ r, double *__restrict__ partial, int nblk)
+{
+    __shared__ double sm[8];
+    if (s->done) return;
+    const double pw = s->pw;
+    if (pw == 0.) return;                      // KSP_DIVERGED_INDEFINITE_MAT, flagged by k_cg_scalars_iter
+    const double a = s->beta / pw;
+    double zz = 0., zr = 0.;
+    for (int64_t ln = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; ln < g.nloc; ln += (int64_t)gridDim.x * blockDim.x) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            int64_t q = d * g.S + g.G + ln;
+            x[q] = fma(a, p[q], x[q]);
+            double rv = fma(-a, w[q], r[q]);
+            r[q] = rv;
+            double z = rv * dinv[q];
+            zz = fma(z, z, zz); zr = fma(z, rv, zr);
+        }
+    }
+    double s0 = block_sum<8>(zz, sm), s1 = block_sum<8>(zr, sm);
+    if (threadIdx.x == 0) { partial[blockIdx.x] = s0; partial[nblk + blockIdx.x] = s1; }
+}
+
+// after the p.w reduction: store it (and flag an indefinite matrix)
+__global__ void k_cg_scalars_pw(CgScalars *s, const double *sum)
+{
+    if (s->done) return;
+    s->pw = sum[0];
+    s->its += 1;                               // ksp->its = i+1 at the top of the loop body
+    if (s->pw == 0.) { s->done = 1; s->reason = -10; }
+}
+
+// after the (z.z, z.r) reduction: convergence test and beta rotation
+__global__ void k_cg_scalars_iter(CgScalars *s, const double *sums)
+{
+    if (s->done) return;
+    double dp = sqrt(sums[0]);
+    s->dp = dp;
+    if (dp <= s->ttol) { s->done = 1; s->reason = dp <= s->abstol ? 3 : 2; return; }
+    if (dp >= s->dtol * s->dp0) { s->done = 1; s->reason = -4; return; }
+    if (s->its >= s->maxits) { s->done = 1; s->reason = -3; return; }
+    s->betaold = s->beta;
+    s->beta = sums[1];
+    if (s->beta == 0.) { s->its += 1; s->done = 1; s->reason = 3; }   // KSP_CONVERGED_ATOL at the next top
+}
+
+// reduce two partial arrays at once: out[0], out[1]
+__global__ void k_reduce2(const double *__restrict__ partial, int nblk, double *__restrict__ out)
+{
+    __shared__ double sm[8];
+    double s0 = 0., s1 = 0.;
+    for (int q = threadIdx.x; q < nblk; q += blockDim.x) { s0 += partial[q]; s1 += partial[nblk + q]; }
+    s0 = block_sum<8>(s0, sm);
+    s1 = block_sum<8>(s1, sm);
+    if (threadIdx.x == 0) { out[0] = s0; out[1] = s1; }
+}
+
+}  // namespace macroc

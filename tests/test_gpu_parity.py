@@ -1,0 +1,189 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU
+oracle on the same inputs.  Tolerances are BASELINE.json's north_star: matrix
+entries and residual vectors 1e-12 relative, displacement 1e-9 relative, Newton
+iteration counts identical (CG counts +-1 by reduction order)."""
+import numpy as np
+import pytest
+
+import macroc_b200 as M
+from oracle import oracle as O
+from helpers import (cfg_kwargs_from_flags, csr_to_block_stencil, golden_cases, load_golden, newton_driver,
+                     rel_err)
+
+pytestmark = pytest.mark.gpu
+
+TOL_MAT = 1e-12
+TOL_RES = 1e-12
+TOL_U = 1e-9
+
+GRIDS = [
+    # (NX, NY, NZ, bc, lengths)
+    (4, 4, 2, M.BC_BENDING, {}),                       # README example / BASELINE configs[0]
+    (4, 4, 2, M.BC_CIRCLE, {}),
+    (5, 2, 2, M.BC_BENDING, {}),                       # tests/CMakeLists.txt:21-24,32
+    (3, 3, 3, M.BC_BENDING, {}),                       # :30
+    (4, 4, 4, M.BC_CIRCLE, {}),                        # :31
+    (5, 3, 5, M.BC_BENDING, {}),                       # :28
+    (2, 2, 2, M.BC_BENDING, {}),                       # smallest legal grid (one element)
+    (33, 5, 4, M.BC_BENDING, dict(lx=10., ly=1., lz=1.)),   # ragged: nodes % 32 != 0, rows wrap inside tiles
+    (9, 3, 9, M.BC_CIRCLE, dict(lx=4., lz=4.)),        # circle actually loads nodes
+    (40, 3, 40, M.BC_CIRCLE, {}),                      # the reference's default grid (macroc.h:44-49)
+    (24, 10, 12, M.BC_BENDING, dict(lx=10., ly=1., lz=1.)),
+]
+
+
+def pair(NX, NY, NZ, bc, extra, **kw):
+    o = O.Oracle(O.Config(NX=NX, NY=NY, NZ=NZ, bc_type=bc, faithful_ke=0, **extra, **kw))
+    m = M.MacroC(M.Config(NX=NX, NY=NY, NZ=NZ, bc_type=bc, **extra,
+                          **{k.replace("rtol", "ksp_rtol") if k == "rtol" else k: v for k, v in kw.items()}))
+    return o, m
+
+
+@pytest.mark.parametrize("NX,NY,NZ,bc,extra", GRIDS)
+def test_one_newton_step_function_by_function(NX, NY, NZ, bc, extra):
+    o, m = pair(NX, NY, NZ, bc, extra)
+    rng = np.random.default_rng(7)
+    # start from a non-trivial state so the residual exercises every element
+    u0 = 1e-3 * rng.standard_normal(o.ndof)
+    o.set_vec("u", u0); m.set_vec(M.VEC_U, u0)
+    U = o.get_displacement(3)
+    assert m.get_displacement(3) == U
+    o.apply_bc_on_u(U); m.apply_bc_on_u(U)
+    assert np.array_equal(m.get_vec(M.VEC_U), o.get_vec("u"))                 # exact: pure scatter
+
+    o.set_strains(); o.homogenize(); m.set_strains(materialize=True)
+    eps, sig = m.get_strain_stress()
+    assert rel_err(eps, o.strain(0)) < 1e-13 and rel_err(sig, o.stress(0)) < 1e-13
+
+    n_o = o.assembly_res(); n_m = m.assembly_res()
+    assert rel_err(m.get_vec(M.VEC_B), o.get_vec("b")) < TOL_RES
+    assert n_m == pytest.approx(n_o, rel=1e-12)
+
+    o.assembly_jac(); m.assembly_jac()
+    A_o = o.block_stencil(); A_m = m.get_matrix_blocks()
+    assert rel_err(A_m, A_o) < TOL_MAT
+    assert np.array_equal(A_m, A_o), "assembled operator is expected to be bitwise the oracle's"
+
+    x = rng.standard_normal(o.ndof)
+    y_o = o.matmult(x)
+    assert rel_err(m.matmult(x, M.OP_ASSEMBLED), y_o) < 1e-13
+    assert rel_err(m.matmult(x, M.OP_MATRIX_FREE), y_o) < 1e-13               # matrix-free == assembled
+
+    its_o, rn_o = o.solve(); its_m, rn_m = m.solve_Ax()
+    assert abs(its_m - its_o) <= 1
+    assert rel_err(m.get_vec(M.VEC_DU), o.get_vec("du")) < 1e-7               # one CG iterate apart at most
+    if its_m == its_o:
+        assert rn_m == pytest.approx(rn_o, rel=1e-6)
+    assert m.ksp_reason() in (2, 3)
+    o.update_u(); m.update_u()
+    assert rel_err(m.get_vec(M.VEC_U), o.get_vec("u")) < 1e-7
+    assert m.calc_force() == pytest.approx(o.calc_force(), rel=1e-6, abs=1e-6 * abs(n_o))
+
+
+@pytest.mark.parametrize("NX,NY,NZ,bc,extra", GRIDS)
+@pytest.mark.parametrize("op", [M.OP_ASSEMBLED, M.OP_MATRIX_FREE])
+def test_time_loop_parity(NX, NY, NZ, bc, extra, op):
+    """main.c:49-82 end to end with a tight KSP tolerance so that both solvers
+    converge to the same displacement: u within 1e-9, Newton counts identical."""
+    ts = 3
+    o = O.Oracle(O.Config(NX=NX, NY=NY, NZ=NZ, bc_type=bc, ts=ts, rtol=1e-12, faithful_ke=0, **extra))
+    m = M.MacroC(M.Config(NX=NX, NY=NY, NZ=NZ, bc_type=bc, ts=ts, ksp_rtol=1e-12, op=op, **extra))
+    logs = o.run()
+    for t in range(ts):
+        r = m.time_step(t)
+        assert r["newton_its"] == logs[t].newton_its
+        assert len(r["res_norm"]) == len(logs[t].res_norm)
+        if logs[t].res_norm[0] > 0:
+            assert r["res_norm"][0] == pytest.approx(logs[t].res_norm[0], rel=1e-9)
+        for a, b in zip(r["ksp_its"], logs[t].ksp_its):
+            assert abs(a - b) <= 2
+    assert rel_err(m.get_vec(M.VEC_U), o.get_vec("u")) < TOL_U
+
+
+@pytest.mark.parametrize("NX,NY,NZ,bc,extra", GRIDS[:9])
+def test_default_tolerance_iteration_counts(NX, NY, NZ, bc, extra):
+    """With the reference's rtol = 1e-5 the iteration history must be the same:
+    identical Newton counts, CG counts +-1, |RES| lines to 1e-6."""
+    ts = 3
+    o = O.Oracle(O.Config(NX=NX, NY=NY, NZ=NZ, bc_type=bc, ts=ts, faithful_ke=0, **extra))
+    m = M.MacroC(M.Config(NX=NX, NY=NY, NZ=NZ, bc_type=bc, ts=ts, **extra))
+    logs = o.run()
+    for t in range(ts):
+        r = m.time_step(t)
+        assert r["newton_its"] == logs[t].newton_its
+        assert all(abs(a - b) <= 1 for a, b in zip(r["ksp_its"], logs[t].ksp_its))
+        assert r["res_norm"][0] == pytest.approx(logs[t].res_norm[0], rel=1e-9, abs=1e-300)
+
+
+@pytest.mark.parametrize("name", golden_cases())
+def test_against_reference_golden_fixtures(name):
+    """Fixtures produced by the reference's own sources (tests/golden/make_golden.py)."""
+    z, kv = load_golden(name)
+    kw = cfg_kwargs_from_flags(kv)
+    NX, NY, NZ = kw["NX"], kw["NY"], kw["NZ"]
+    m = M.MacroC(M.Config(**kw))
+    seen = {}
+    def cap(time_s, it, stage):
+        if stage == "pre_solve":
+            seen["b"] = m.get_vec(M.VEC_B); seen["A"] = m.get_matrix_blocks()
+        else:
+            seen["x"] = m.get_vec(M.VEC_DU)
+    log = newton_driver(m, kw["ts"], capture=cap)
+    res = [r for l in log for r in l["res_norm"]]
+    kits = [i for l in log for i in l["ksp_its"]]
+    assert len(res) == len(z["res_norms"]) and len(kits) == len(z["ksp_its"])
+    for a, b in zip(res, z["res_norms"]):
+        # first residual of a step is O(1e6): printed digits; converged ones are noise-level
+        if b > 1.0:
+            assert a == pytest.approx(b, rel=1e-5)
+    assert all(abs(int(a) - int(b)) <= 1 for a, b in zip(kits, z["ksp_its"]))
+    A_ref = csr_to_block_stencil(z["rowptr"], z["col"], z["val"], NX, NY, NZ)
+    assert rel_err(seen["A"], A_ref) < TOL_MAT
+    assert rel_err(seen["b"], z["b"]) < 1e-7       # b depends on the previous CG iterate (rtol 1e-5)
+    assert rel_err(m.get_vec(M.VEC_U), z["u"]) < 1e-4   # rtol-1e-5 solves: agreement to solver tolerance
+
+
+def test_cantilever_config_c2_parity():
+    """BASELINE configs[1]: 128x32x32, lx=10, ly=lz=1, bending (393 216 DOF)."""
+    kw = dict(NX=128, NY=32, NZ=32, lx=10., ly=1., lz=1., bc_type=M.BC_BENDING)
+    o = O.Oracle(O.Config(faithful_ke=0, nthreads=1, **kw))
+    m = M.MacroC(M.Config(**kw))
+    U = o.get_displacement(1)
+    o.apply_bc_on_u(U); m.apply_bc_on_u(U)
+    o.set_strains(); o.homogenize(); m.set_strains()
+    n_o = o.assembly_res(); n_m = m.assembly_res()
+    assert n_m == pytest.approx(n_o, rel=1e-12)
+    assert rel_err(m.get_vec(M.VEC_B), o.get_vec("b")) < TOL_RES
+    o.assembly_jac(); m.assembly_jac()
+    assert np.array_equal(m.get_matrix_blocks(), o.block_stencil())
+    x = np.sin(0.37 * np.arange(o.ndof)) + 0.1
+    y = o.matmult(x)
+    assert rel_err(m.matmult(x, M.OP_ASSEMBLED), y) < 1e-13
+    assert rel_err(m.matmult(x, M.OP_MATRIX_FREE), y) < 1e-13
+    its_o, _ = o.solve(); its_m, _ = m.solve_Ax()
+    assert abs(its_o - its_m) <= 1
+    assert rel_err(m.get_vec(M.VEC_DU), o.get_vec("du")) < 1e-6
+
+
+def test_large_grid_properties():
+    """Size-independent properties at a grid the oracle cannot hold (160^3 nodes,
+    12.3M DOF): symmetry <x, A y> == <y, A x>, rigid translations in the null
+    space of the unconstrained rows, assembled == matrix-free, Dirichlet rows
+    act as identity, linearity."""
+    N = 160
+    m = M.MacroC(M.Config(NX=N, NY=N, NZ=N, bc_type=M.BC_BENDING, lx=1., ly=1., lz=1.))
+    m.assembly_jac()
+    n = m.local_ndof
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal(n); y = rng.standard_normal(n)
+    Ax = m.matmult(x); Ay = m.matmult(y)
+    assert abs(np.dot(y, Ax) - np.dot(x, Ay)) < 1e-11 * abs(np.dot(y, Ax))
+    assert rel_err(m.matmult(x, M.OP_MATRIX_FREE), Ax) < 1e-13
+    assert rel_err(m.matmult(2.5 * x - y), 2.5 * Ax - Ay) < 1e-13
+    # Dirichlet dofs (faces X=0 and X=LX): identity rows/cols
+    x3 = x.reshape(N, N, N, 3); Ax3 = Ax.reshape(N, N, N, 3)
+    assert np.array_equal(Ax3[:, :, 0, :], x3[:, :, 0, :]) and np.array_equal(Ax3[:, :, -1, :], x3[:, :, -1, :])
+    # rigid translation: zero force on rows that do not couple to a Dirichlet node
+    t = np.zeros((N, N, N, 3)); t[..., 1] = 1.0
+    At = m.matmult(t.reshape(-1)).reshape(N, N, N, 3)
+    assert np.abs(At[:, :, 2:-2, :]).max() < 1e-9 * 8.0e7 * m.cfg.lx / (N - 1)
