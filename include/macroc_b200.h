@@ -143,6 +143,15 @@ int macroc_get_strain_stress(macroc_ctx *ctx, double *strain, double *stress, in
  * between launches. */
 int macroc_time_kernel(macroc_ctx *ctx, int what, int reps, int flush_l2, double *ms_mean);
 uint64_t macroc_launch_count(const macroc_ctx *ctx);       /* kernels launched so far */
+/* CUDA-event stopwatch on the context's stream (slots 0..7): record, then
+ * elapsed(a, b) synchronises on b and returns the device time between them. */
+int macroc_event_record(macroc_ctx *ctx, int slot);
+int macroc_event_elapsed_ms(macroc_ctx *ctx, int slot_a, int slot_b, double *ms);
+/* Live profile of the dominant kernel: while enabled, every `stride`-th operator
+ * application inside solve_Ax is bracketed by CUDA events on the launch stream;
+ * get returns the mean device time per application and the sample count. */
+int macroc_profile_enable(macroc_ctx *ctx, int enable, int stride);
+int macroc_profile_get(macroc_ctx *ctx, double *apply_ms_mean, int64_t *samples);
 int macroc_device_synchronize(macroc_ctx *ctx);
 int macroc_version(void);
 

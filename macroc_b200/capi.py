@@ -32,6 +32,7 @@ EXPORTS = [
     "macroc_calc_force", "macroc_time_step", "macroc_local_ndof", "macroc_global_ndof", "macroc_set_vec",
     "macroc_get_vec", "macroc_get_matrix_blocks", "macroc_matmult", "macroc_get_strain_stress",
     "macroc_time_kernel", "macroc_launch_count", "macroc_device_synchronize", "macroc_version",
+    "macroc_event_record", "macroc_event_elapsed_ms", "macroc_profile_enable", "macroc_profile_get",
 ]
 
 
@@ -118,6 +119,10 @@ def lib():
     L.macroc_time_kernel.argtypes = [vp, C.c_int, C.c_int, C.c_int, dp]
     L.macroc_launch_count.argtypes = [vp]; L.macroc_launch_count.restype = C.c_uint64
     L.macroc_device_synchronize.argtypes = [vp]
+    L.macroc_event_record.argtypes = [vp, C.c_int]
+    L.macroc_event_elapsed_ms.argtypes = [vp, C.c_int, C.c_int, dp]
+    L.macroc_profile_enable.argtypes = [vp, C.c_int, C.c_int]
+    L.macroc_profile_get.argtypes = [vp, dp, C.POINTER(C.c_int64)]
     L.macroc_version.restype = C.c_int
     _lib = L
     return L
@@ -343,6 +348,22 @@ class MacroC:
         ms = C.c_double()
         self._chk(self._L.macroc_time_kernel(self._h, what, reps, int(flush_l2), C.byref(ms)))
         return ms.value
+
+    def event_record(self, slot: int):
+        self._chk(self._L.macroc_event_record(self._h, slot))
+
+    def event_elapsed_ms(self, a: int, b: int) -> float:
+        ms = C.c_double()
+        self._chk(self._L.macroc_event_elapsed_ms(self._h, a, b, C.byref(ms)))
+        return ms.value
+
+    def profile_enable(self, enable: bool = True, stride: int = 8):
+        self._chk(self._L.macroc_profile_enable(self._h, int(enable), stride))
+
+    def profile_get(self):
+        ms, n = C.c_double(), C.c_int64()
+        self._chk(self._L.macroc_profile_get(self._h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
 
     def launch_count(self) -> int:
         return int(self._L.macroc_launch_count(self._h))

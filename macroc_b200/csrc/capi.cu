@@ -57,6 +57,14 @@ struct macroc_ctx {
     uint64_t launches = 0;
     int ksp_reason = 0;
     int vec_blocks = 0, spmv_blocks = 0;
+    cudaEvent_t ev_user[8] = {nullptr};
+    // live profile of the operator application (ring of event pairs)
+    static constexpr int PROF_RING = 128;
+    cudaEvent_t prof_ev[2 * PROF_RING] = {nullptr};
+    bool prof_on = false;
+    int prof_stride = 1, prof_used = 0;
+    int64_t prof_counter = 0, prof_samples = 0;
+    double prof_ms = 0.;
     std::string err;
 };
 
@@ -230,6 +238,8 @@ static int ctx_free(macroc_ctx *c)
     if (c->sc_host) cudaFreeHost(c->sc_host);
     for (cudaEvent_t e : {c->ev_ready, c->ev_halo, c->ev_t0, c->ev_t1, c->ev_chk[0], c->ev_chk[1]})
         if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : c->ev_user) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : c->prof_ev) if (e) cudaEventDestroy(e);
     if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -263,6 +273,7 @@ extern "C" int macroc_create(const macroc_config *cfg, int rank, int nranks, con
     CUC(cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking));
     for (cudaEvent_t *e : {&c->ev_ready, &c->ev_halo, &c->ev_chk[0], &c->ev_chk[1]}) CUC(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
     CUC(cudaEventCreate(&c->ev_t0)); CUC(cudaEventCreate(&c->ev_t1));
+    for (cudaEvent_t &e : c->ev_user) CUC(cudaEventCreate(&e));
 
     GridDev &g = c->g;
     g.NX = slab.NX; g.NY = slab.NY; g.NZ = slab.NZ; g.zs = slab.zs; g.nzl = slab.nzl;
@@ -516,8 +527,11 @@ static int cg_iteration(macroc_ctx *c, int op)
     const GridDev &g = c->g;
     const int nb = c->vec_blocks;
     LAUNCH(c, k_cg_update_p, nb, 256, g, c->sc, c->vec[V_R], c->vec[V_DINV], c->vec[V_P]);
+    const bool sample = c->prof_on && c->prof_used < macroc_ctx::PROF_RING && (c->prof_counter++ % c->prof_stride) == 0;
+    if (sample) CU(c, cudaEventRecord(c->prof_ev[2 * c->prof_used], c->stream));
     int rc = apply_operator(c, op, c->vec[V_P], c->vec[V_W], true, &c->sc->done);
     if (rc) return rc;
+    if (sample) { CU(c, cudaEventRecord(c->prof_ev[2 * c->prof_used + 1], c->stream)); c->prof_used++; }
     rc = allreduce_sums(c, 1);
     if (rc) return rc;
     LAUNCH(c, k_cg_scalars_pw, 1, 1, c->sc, c->sums);
@@ -577,6 +591,17 @@ extern "C" int macroc_solve_Ax(macroc_ctx *c, int *its, double *rnorm)
     }
     CU(c, cudaMemcpyAsync(&c->sc_host[0], c->sc, sizeof(CgScalars), cudaMemcpyDeviceToHost, c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
+    if (c->prof_on) {
+        // samples taken after convergence bracket no-op launches: keep the first `its` only
+        int64_t stride = c->prof_stride;
+        for (int q = 0; q < c->prof_used; ++q) {
+            if ((int64_t)q * stride >= c->sc_host[0].its) break;
+            float ms = 0.f;
+            CU(c, cudaEventElapsedTime(&ms, c->prof_ev[2 * q], c->prof_ev[2 * q + 1]));
+            c->prof_ms += ms; c->prof_samples++;
+        }
+        c->prof_used = 0; c->prof_counter = 0;
+    }
     if (its) *its = c->sc_host[0].its;
     if (rnorm) *rnorm = c->sc_host[0].dp;       // KSPGetResidualNorm: last preconditioned norm
     c->ksp_reason = c->sc_host[0].reason;
@@ -749,6 +774,45 @@ extern "C" int macroc_get_strain_stress(macroc_ctx *c, double *strain, double *s
 // ---------------------------------------------------------------------------
 
 extern "C" uint64_t macroc_launch_count(const macroc_ctx *c) { return c ? c->launches : 0; }
+
+extern "C" int macroc_event_record(macroc_ctx *c, int slot)
+{
+    if (!c || slot < 0 || slot >= 8) return MACROC_ERR_ARG;
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaEventRecord(c->ev_user[slot], c->stream));
+    return MACROC_OK;
+}
+
+extern "C" int macroc_event_elapsed_ms(macroc_ctx *c, int a, int b, double *ms)
+{
+    if (!c || !ms || a < 0 || a >= 8 || b < 0 || b >= 8) return MACROC_ERR_ARG;
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaEventSynchronize(c->ev_user[b]));
+    float f = 0.f;
+    CU(c, cudaEventElapsedTime(&f, c->ev_user[a], c->ev_user[b]));
+    *ms = f;
+    return MACROC_OK;
+}
+
+extern "C" int macroc_profile_enable(macroc_ctx *c, int enable, int stride)
+{
+    if (!c) return MACROC_ERR_ARG;
+    CU(c, cudaSetDevice(c->device));
+    if (enable && !c->prof_ev[0])
+        for (cudaEvent_t &e : c->prof_ev) CU(c, cudaEventCreate(&e));
+    c->prof_on = enable != 0;
+    c->prof_stride = stride > 0 ? stride : 1;
+    c->prof_used = 0; c->prof_counter = 0; c->prof_samples = 0; c->prof_ms = 0.;
+    return MACROC_OK;
+}
+
+extern "C" int macroc_profile_get(macroc_ctx *c, double *apply_ms_mean, int64_t *samples)
+{
+    if (!c) return MACROC_ERR_ARG;
+    if (apply_ms_mean) *apply_ms_mean = c->prof_samples ? c->prof_ms / (double)c->prof_samples : 0.;
+    if (samples) *samples = c->prof_samples;
+    return MACROC_OK;
+}
 
 extern "C" int macroc_device_synchronize(macroc_ctx *c)
 {
