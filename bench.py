@@ -249,7 +249,10 @@ def run_gpu_arm(args):
 
     nx, ny, nz, nd, nb = workload(world, args.grid)
     op = M.OP_MATRIX_FREE if args.matrix_free else M.OP_ASSEMBLED
-    cfg = M.Config(NX=nx, NY=ny, NZ=nz, pz=world, lx=1.0, ly=1.0, lz=1.0 * world, bc_type=M.BC_BENDING,
+    # the reference's default lengths (macroc.h:47-49), lz grows with the slab count so dz is fixed;
+    # the element matrix is the unit-cube one scaled by wg, so CG counts do not
+    # depend on the lengths -- they only keep |RES| above the absolute Newton tolerance 1e-1
+    cfg = M.Config(NX=nx, NY=ny, NZ=nz, pz=world, lx=50.0, ly=1.0, lz=50.0 * world, bc_type=M.BC_BENDING,
                    ts=args.steps + args.warmup + 1, device=local_rank, op=op)
     m = M.MacroC(cfg, rank=rank, nranks=world, unique_id=uid)
     nloc = m.local_ndof
