@@ -1,0 +1,142 @@
+"""Multi-rank worker launched by torch.distributed.run (test infrastructure).
+
+--mode host (gloo, CPU): every rank asks the C-ABI library for its z-slab, Dirichlet lists
+  and the bench's per-rank byte accounting; the ranks all_gather them and check that the
+  slabs tile the grid, that neighbours agree on the halo plane, that the merged Dirichlet
+  lists equal the single-rank list (the reference's decomposition-independence invariant).
+--mode gpu (nccl): every rank owns one GPU, runs the time loop on its slab (NCCL halos and
+  all-reduces inside the library), the slabs are gathered and rank 0 checks them against the
+  single-rank CPU oracle.
+"""
+import argparse
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import macroc_b200 as M  # noqa: E402
+
+
+def gather_objects(obj):
+    out = [None] * dist.get_world_size()
+    dist.all_gather_object(out, obj)
+    return out
+
+
+def host_mode(args):
+    rank, world = dist.get_rank(), dist.get_world_size()
+    for (NX, NY, NZ) in [(5, 2, 2), (6, 4, 9), (16, 8, 7)]:
+        if world > NZ:
+            continue
+        for bc in (M.BC_BENDING, M.BC_CIRCLE):
+            cfg = M.Config(NX=NX, NY=NY, NZ=NZ, bc_type=bc, lx=5.0, lz=6.0)
+            part = M.partition(cfg, rank, world)
+            idx, coef = M.bc_lists(cfg, rank, world)
+            parts = gather_objects(part)
+            lists = gather_objects((idx, coef))
+            # slabs tile [0, NZ) in rank order, element layers tile [0, NZ-1)
+            z = 0
+            ez = 0
+            for r, p in enumerate(parts):
+                xs, ys, zs, xm, ym, zm = p["corners"]
+                assert (xs, ys, xm, ym) == (0, 0, NX, NY) and zs == z
+                z += zm
+                Xs, Ys, Zs, Xm, Ym, Zm = p["ghost_corners"]
+                assert Zs == max(zs - 1, 0) and Zs + Zm == min(zs + zm + 1, NZ)
+                assert p["elements_sizes"][:2] == (NX - 1, NY - 1)
+                ez += p["elements_sizes"][2]
+            assert z == NZ and ez == NZ - 1
+            # halo agreement: my upper ghost plane is my upper neighbour's first owned plane
+            if rank + 1 < world:
+                up = parts[rank + 1]["corners"]
+                me = part["ghost_corners"]
+                assert me[2] + me[5] - 1 == up[2]
+            # merged Dirichlet lists == single-rank list (values too)
+            merged = {}
+            for ix, cf in lists:
+                for i, c in zip(ix, cf):
+                    if i >= 0:
+                        assert merged.setdefault(int(i), float(c)) == float(c)
+            ix1, cf1 = M.bc_lists(cfg, 0, 1)
+            single = {int(i): float(c) for i, c in zip(ix1, cf1) if i >= 0}
+            assert merged == single, (NX, NY, NZ, bc)
+    # bench.py's max/sum-over-ranks helpers on the gloo backend
+    t = torch.tensor([float(rank + 1)], dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    assert t.item() == world
+    if rank == 0:
+        print("HOST-OK")
+
+
+def gpu_mode(args):
+    from oracle import oracle as O
+    from helpers import rel_err
+    rank, world = dist.get_rank(), dist.get_world_size()
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    cases = [(8, 5, 2 * world + 1, M.BC_BENDING, {}), (40, 3, 40, M.BC_CIRCLE, {}),
+             (33, 9, 4 * world + 3, M.BC_BENDING, dict(lx=10., ly=1., lz=1.)),
+             (9, 3, max(9, world), M.BC_CIRCLE, dict(lx=4., lz=4.))]
+    for (NX, NY, NZ, bc, extra) in cases:
+        for op in (M.OP_ASSEMBLED, M.OP_MATRIX_FREE):
+            box = [M.get_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(box, src=0)
+            ts = 3
+            cfg = M.Config(NX=NX, NY=NY, NZ=NZ, bc_type=bc, pz=world, ts=ts, ksp_rtol=1e-12, op=op, device=local, **extra)
+            m = M.MacroC(cfg, rank=rank, nranks=world, unique_id=box[0])
+            logs = [m.time_step(t) for t in range(ts)]
+            u_loc = m.get_vec(M.VEC_U)
+            force = m.calc_force()
+            x = np.sin(0.37 * np.arange(3 * NX * NY * NZ)) + 0.1
+            p = M.partition(cfg, rank, world)
+            zs, zm = p["corners"][2], p["corners"][5]
+            sl = slice(3 * NX * NY * zs, 3 * NX * NY * (zs + zm))
+            if op == M.OP_ASSEMBLED:
+                m.assembly_jac()
+            y_loc = m.matmult(x[sl], op)
+            A_loc = m.get_matrix_blocks() if op == M.OP_ASSEMBLED else None
+            got = gather_objects((u_loc, y_loc, A_loc, logs, force))
+            m.close()
+            if rank == 0:
+                o = O.Oracle(O.Config(NX=NX, NY=NY, NZ=NZ, bc_type=bc, ts=ts, rtol=1e-12, faithful_ke=0, **extra))
+                ologs = o.run()
+                u = np.concatenate([g[0] for g in got]); y = np.concatenate([g[1] for g in got])
+                assert rel_err(u, o.get_vec("u")) < 1e-9, (NX, NY, NZ, bc, op, rel_err(u, o.get_vec("u")))
+                o.assembly_jac()
+                assert rel_err(y, o.matmult(x)) < 1e-13
+                if op == M.OP_ASSEMBLED:
+                    A = np.concatenate([g[2] for g in got])
+                    assert np.array_equal(A, o.block_stencil())
+                for g in got:
+                    assert [l["newton_its"] for l in g[3]] == [l.newton_its for l in ologs]
+                    assert g[3] == got[0][3]                 # every rank saw the same history
+                    assert abs(g[4] - ologs[-1].force) <= 1e-6 * abs(ologs[-1].force) + 1e-9
+            dist.barrier()
+    if rank == 0:
+        print("GPU-OK")
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--mode", choices=["host", "gpu"], required=True)
+    args = ap.parse_args()
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    if args.mode == "host":
+        dist.init_process_group("gloo")
+        host_mode(args)
+    else:
+        local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        gpu_mode(args)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
