@@ -20,6 +20,7 @@
 #include "../../include/macroc_b200.h"
 #include "grid.h"
 #include "kernels.cuh"
+#include "spmv_tma.cuh"
 
 using namespace macroc;
 
@@ -57,6 +58,7 @@ struct macroc_ctx {
     uint64_t launches = 0;
     int ksp_reason = 0;
     int vec_blocks = 0, spmv_blocks = 0;
+    int spmv_variant = 10;           // 10: TMA ring 8 warps x 4 stages (default); 0/1: per-lane LDG; see spmv_launch
     cudaEvent_t ev_user[8] = {nullptr};
     // live profile of the operator application (ring of event pairs)
     static constexpr int PROF_RING = 128;
@@ -265,6 +267,7 @@ extern "C" int macroc_create(const macroc_config *cfg, int rank, int nranks, con
     }
     macroc_ctx *c = new macroc_ctx();
     c->cfg = *cfg; c->slab = slab; c->geo = make_geometry(*cfg);
+    if (const char *v = getenv("MACROC_SPMV_VARIANT")) c->spmv_variant = atoi(v);
     if (cfg->device >= 0) c->device = cfg->device;
     else if (cudaGetDevice(&c->device) != cudaSuccess) c->device = 0;
 #define CUC(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { g_last_error = std::string(#call) + " -> " + cudaGetErrorString(_e); ctx_free(c); return MACROC_ERR_CUDA; } } while (0)
@@ -468,6 +471,53 @@ extern "C" int macroc_assembly_jac(macroc_ctx *c)
     return MACROC_OK;
 }
 
+template <int WARPS, int NSTAGE>
+static int spmv_launch_tma(macroc_ctx *c, double *p, double *w, int64_t first, int64_t count, double *partial,
+                           bool with_dot, const int *done)
+{
+    using SM = SpmvTmaSmem<WARPS, NSTAGE>;
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(k_spmv_tma<WARPS, NSTAGE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::total);
+        cudaFuncSetAttribute(k_spmv_tma<WARPS, NSTAGE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::total);
+        configured = true;
+    }
+    int per_sm = std::max(1, (227 * 1024) / (SM::total + 1024));
+    int blocks = (int)std::min<int64_t>(cdiv64(count, WARPS), (int64_t)148 * per_sm);
+    if (with_dot) k_spmv_tma<WARPS, NSTAGE, true><<<blocks, WARPS * 32, SM::total, c->stream>>>(c->g, c->A, p, w, first, count, partial, done);
+    else k_spmv_tma<WARPS, NSTAGE, false><<<blocks, WARPS * 32, SM::total, c->stream>>>(c->g, c->A, p, w, first, count, partial, done);
+    c->launches++;
+    return blocks;
+}
+
+// one assembled SpMV launch over tiles [first, first+count); returns the number of partials written
+static int spmv_launch(macroc_ctx *c, double *p, double *w, int64_t first, int64_t count, double *partial,
+                       bool with_dot, const int *done)
+{
+    const GridDev &g = c->g;
+    switch (c->spmv_variant) {
+        case 10: return spmv_launch_tma<8, 4>(c, p, w, first, count, partial, with_dot, done);
+        case 11: return spmv_launch_tma<8, 5>(c, p, w, first, count, partial, with_dot, done);
+        case 12: return spmv_launch_tma<4, 8>(c, p, w, first, count, partial, with_dot, done);
+        case 13: return spmv_launch_tma<4, 12>(c, p, w, first, count, partial, with_dot, done);
+        case 14: return spmv_launch_tma<6, 6>(c, p, w, first, count, partial, with_dot, done);
+        case 15: return spmv_launch_tma<4, 4>(c, p, w, first, count, partial, with_dot, done);
+        case 16: return spmv_launch_tma<12, 4>(c, p, w, first, count, partial, with_dot, done);
+        case 1: {
+            int blocks = (int)std::min<int64_t>(cdiv64(count, 8), 148 * 8);
+            if (with_dot) LAUNCH(c, (k_spmv<true, 4>), blocks, 256, g, c->A, p, w, first, count, partial, done);
+            else LAUNCH(c, (k_spmv<false, 4>), blocks, 256, g, c->A, p, w, first, count, partial, done);
+            return blocks;
+        }
+        default: {
+            int blocks = (int)std::min<int64_t>(cdiv64(count, 8), 148 * 8);
+            if (with_dot) LAUNCH(c, (k_spmv<true, 1>), blocks, 256, g, c->A, p, w, first, count, partial, done);
+            else LAUNCH(c, (k_spmv<false, 1>), blocks, 256, g, c->A, p, w, first, count, partial, done);
+            return blocks;
+        }
+    }
+}
+
 // w = A p on the context's stream; p's halo is exchanged on comm_stream while
 // the rows that do not touch a ghost plane are computed.
 static int apply_operator(macroc_ctx *c, int op, double *p, double *w, bool with_dot, const int *done)
@@ -503,9 +553,7 @@ static int apply_operator(macroc_ctx *c, int op, double *p, double *w, bool with
             if (with_dot) LAUNCH(c, k_apply_mf<true>, blocks, 256, g, c->T, c->nodemask, p, w, first, count, c->partial + nparts, done);
             else LAUNCH(c, k_apply_mf<false>, blocks, 256, g, c->T, c->nodemask, p, w, first, count, c->partial + nparts, done);
         } else {
-            blocks = (int)std::min<int64_t>(cdiv64(count, 8), 148 * 8);
-            if (with_dot) LAUNCH(c, k_spmv<true>, blocks, 256, g, c->A, p, w, first, count, c->partial + nparts, done);
-            else LAUNCH(c, k_spmv<false>, blocks, 256, g, c->A, p, w, first, count, c->partial + nparts, done);
+            blocks = spmv_launch(c, p, w, first, count, c->partial + nparts, with_dot, done);
         }
         nparts += blocks;
     };

@@ -215,8 +215,8 @@ k_fill_operator(GridDev g, const double *__restrict__ T, const uint8_t *__restri
 // Assembled block-stencil SpMV  w = A p  (+ fused partial of p.w)
 // HBM bound: 1 952 B of operator per node against 48 B of vectors.
 // ---------------------------------------------------------------------------
-template <bool DOT>
-__global__ void __launch_bounds__(256)
+template <bool DOT, int MINB>
+__global__ void __launch_bounds__(256, MINB)
 k_spmv(GridDev g, const double2 *__restrict__ A, const double *__restrict__ p, double *__restrict__ w,
        int64_t tile0, int64_t ntiles, double *__restrict__ partial, const int *__restrict__ done)
 {

@@ -195,3 +195,26 @@ def test_large_grid_properties():
     t = np.zeros((N, N, N, 3)); t[..., 1] = 1.0
     At = m.matmult(t.reshape(-1)).reshape(N, N, N, 3)
     assert np.abs(At[:, :, 2:-2, :]).max() < 1e-9 * 8.0e7 * m.cfg.lx / (N - 1)
+
+
+@pytest.mark.parametrize("name", ["readme_4x4x2_bending", "ctest_4x4x4_circle", "beam_16x6x6_bending"])
+def test_c_host_driver_log_matches_reference(name, tmp_path):
+    """macroc_b200/lib/macroc (the C host over the C ABI) prints the reference's lines."""
+    import os, re, subprocess
+    z, kv = load_golden(name)
+    exe = os.path.join(os.path.dirname(M.capi.LIB_PATH), "macroc")
+    args = [a for kvp in kv.items() for a in kvp]
+    r = subprocess.run([exe] + args, cwd=tmp_path, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    res = [float(x) for x in re.findall(r"\|RES\| = (\S+)", r.stdout)]
+    ksp = [int(x) for x in re.findall(r"Its = (\d+)", r.stdout)]
+    newton = [int(x) for x in re.findall(r"Newton Iteration = (\d+)", r.stdout)]
+    assert newton == list(z["newton_lines"])
+    assert len(res) == len(z["res_norms"]) and all(abs(a - int(b)) <= 1 for a, b in zip(ksp, z["ksp_its"]))
+    first = 0
+    for t in range(int(kv["-ts"])):
+        n_lines = 1 if z["res_norms"][first] == 0 else 2
+        assert res[first] == pytest.approx(float(z["res_norms"][first]), rel=1e-5, abs=1e-300)
+        first += n_lines
+    info = np.loadtxt(tmp_path / "info.dat", ndmin=2)
+    assert np.allclose(info[:, 3], z["force"], rtol=1e-4, atol=1e-9)
