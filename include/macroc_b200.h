@@ -39,6 +39,11 @@ extern "C" {
 enum { MACROC_BC_BENDING = 0, MACROC_BC_CIRCLE = 1 };          /* include/macroc.h:58 */
 enum { MACROC_VEC_U = 0, MACROC_VEC_DU = 1, MACROC_VEC_B = 2 }; /* include/macroc.h:128 */
 enum { MACROC_OP_ASSEMBLED = 0, MACROC_OP_MATRIX_FREE = 1 };
+/* where the Gauss-point stress / tangent come from (the MicroPP boundary) */
+enum { MACROC_MAT_UNIFORM = 0,   /* sigma = D eps, C = D in registers (north_star's fixed D)    */
+       MACROC_MAT_PER_GP = 1 };  /* device arrays strain/stress[ngp*6], ctan[ngp*36], gpi=ie*8+gp */
+enum { MACROC_JAC_AUTO = 0,      /* uniform D: class-stencil fill; per-GP: element kernel        */
+       MACROC_JAC_ELEMENT = 1 }; /* always the per-element kernel                                 */
 /* KSPConvergedReason values used */
 enum {
     MACROC_KSP_CONVERGED_RTOL = 2, MACROC_KSP_CONVERGED_ATOL = 3,
@@ -67,7 +72,9 @@ typedef struct {
     int32_t op;                    /* MACROC_OP_ASSEMBLED (reference: MATAIJ + MatMult) or
                                       MACROC_OP_MATRIX_FREE for solve_Ax                     */
     int32_t device;                /* CUDA device ordinal, -1 = current                      */
-    int32_t reserved[8];
+    int32_t material;              /* MACROC_MAT_*                                           */
+    int32_t jac_mode;              /* MACROC_JAC_*                                           */
+    int32_t reserved[6];
 } macroc_config;
 
 typedef struct macroc_ctx macroc_ctx;
@@ -107,6 +114,15 @@ int macroc_apply_bc_on_u(macroc_ctx *ctx, double U);                          /*
  * constitutive plug-in / export; the residual kernel recomputes them in
  * registers either way. */
 int macroc_set_strains(macroc_ctx *ctx, int materialize);
+/* micropp_C_homogenize (main.c:62) stand-in for MACROC_MAT_PER_GP: stress = D strain, ctan = D
+ * for every owned Gauss point, on the device.  A GPU material model replaces this call by
+ * writing the arrays of macroc_gp_arrays itself.  No-op for MACROC_MAT_UNIFORM. */
+int macroc_homogenize(macroc_ctx *ctx);
+/* DEVICE pointers to the Gauss-point arrays (gpi = ie*8+gp over the rank's DMDA-owned
+ * elements, assembly.c:58,91,148): strain/stress 6 doubles, ctan 36 doubles per point. */
+int macroc_gp_arrays(macroc_ctx *ctx, double **strain, double **stress, double **ctan, int64_t *n_gp);
+/* host -> device copies into those arrays (tests, CPU material models); NULL = leave as is */
+int macroc_set_gp_data(macroc_ctx *ctx, const double *stress_host, const double *ctan_host);
 int macroc_assembly_res(macroc_ctx *ctx, double *norm);    /* assembly.c:120-176 + VecNorm main.c:67 */
 int macroc_assembly_jac(macroc_ctx *ctx);                  /* assembly.c:69-117 + bcs.c:341-347      */
 int macroc_solve_Ax(macroc_ctx *ctx, int *its, double *rnorm);   /* assembly.c:179-192 (KSPCG+PCJACOBI) */

@@ -21,6 +21,8 @@ CSRC = os.path.join(HERE, "csrc")
 BC_BENDING, BC_CIRCLE = 0, 1
 VEC_U, VEC_DU, VEC_B = 0, 1, 2
 OP_ASSEMBLED, OP_MATRIX_FREE = 0, 1
+MAT_UNIFORM, MAT_PER_GP = 0, 1
+JAC_AUTO, JAC_ELEMENT = 0, 1
 ERR_NO_DEVICE = 97
 
 # every symbol include/macroc_b200.h declares
@@ -33,6 +35,7 @@ EXPORTS = [
     "macroc_get_vec", "macroc_get_matrix_blocks", "macroc_matmult", "macroc_get_strain_stress",
     "macroc_time_kernel", "macroc_launch_count", "macroc_device_synchronize", "macroc_version",
     "macroc_event_record", "macroc_event_elapsed_ms", "macroc_profile_enable", "macroc_profile_get",
+    "macroc_homogenize", "macroc_gp_arrays", "macroc_set_gp_data",
 ]
 
 
@@ -56,7 +59,8 @@ class CConfig(C.Structure):
         ("E", C.c_double), ("nu", C.c_double),
         ("D", C.c_double * 36),
         ("use_D", C.c_int32), ("op", C.c_int32), ("device", C.c_int32),
-        ("reserved", C.c_int32 * 8),
+        ("material", C.c_int32), ("jac_mode", C.c_int32),
+        ("reserved", C.c_int32 * 6),
     ]
 
 
@@ -102,6 +106,10 @@ def lib():
     L.macroc_apply_bc_on_u.argtypes = [vp, C.c_double]
     L.macroc_set_strains.argtypes = [vp, C.c_int]
     L.macroc_assembly_res.argtypes = [vp, dp]
+    L.macroc_homogenize.argtypes = [vp]
+    L.macroc_gp_arrays.argtypes = [vp, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                   C.POINTER(C.c_int64)]
+    L.macroc_set_gp_data.argtypes = [vp, C.c_void_p, C.c_void_p]
     L.macroc_assembly_jac.argtypes = [vp]
     L.macroc_solve_Ax.argtypes = [vp, ip, dp]
     L.macroc_ksp_reason.argtypes = [vp, ip]
@@ -155,6 +163,8 @@ class Config:
     nu: float = 0.25
     op: int = OP_ASSEMBLED
     device: int = -1
+    material: int = MAT_UNIFORM
+    jac_mode: int = JAC_AUTO
     D: np.ndarray | None = None
 
     def to_c(self) -> CConfig:
@@ -162,7 +172,7 @@ class Config:
         lib().macroc_default_config(C.byref(c))
         for k in ("NX", "NY", "NZ", "px", "py", "pz", "lx", "ly", "lz", "bc_type", "ts", "dt", "final_time",
                   "newton_max_its", "newton_min_tol", "newton_rel_tol", "ksp_rtol", "ksp_abstol", "ksp_dtol",
-                  "ksp_maxits", "E", "nu", "op", "device"):
+                  "ksp_maxits", "E", "nu", "op", "device", "material", "jac_mode"):
             setattr(c, k, getattr(self, k))
         if self.D is not None:
             d = np.ascontiguousarray(self.D, dtype=np.float64).reshape(36)
@@ -277,6 +287,21 @@ class MacroC:
         n = C.c_double()
         self._chk(self._L.macroc_assembly_res(self._h, C.byref(n)))
         return n.value
+
+    def homogenize(self):
+        self._chk(self._L.macroc_homogenize(self._h))
+
+    def gp_arrays(self):
+        """Device pointers (ints) of strain, stress, ctan and the number of Gauss points."""
+        a, b, c, n = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_int64()
+        self._chk(self._L.macroc_gp_arrays(self._h, C.byref(a), C.byref(b), C.byref(c), C.byref(n)))
+        return a.value, b.value, c.value, n.value
+
+    def set_gp_data(self, stress: np.ndarray | None = None, ctan: np.ndarray | None = None):
+        s = np.ascontiguousarray(stress, dtype=np.float64) if stress is not None else None
+        t = np.ascontiguousarray(ctan, dtype=np.float64) if ctan is not None else None
+        self._chk(self._L.macroc_set_gp_data(self._h, s.ctypes.data if s is not None else None,
+                                             t.ctypes.data if t is not None else None))
 
     def assembly_jac(self):
         self._chk(self._L.macroc_assembly_jac(self._h))

@@ -1,0 +1,232 @@
+// assembly_elem.cuh -- per-element residual and Jacobian kernels.
+//
+// These are the general form of the reference's element loops
+// (src/assembly.c:85-108 and :142-162): every Gauss point has its own stress
+// (6 doubles) and tangent (36 doubles, row-major) at gpi = ie*8 + gp
+// (assembly.c:58,91,148) -- the arrays a constitutive plug-in in MicroPP's role
+// fills on the device.  With the homogenised linear law they are filled by
+// k_homogenize_linear (stress = D strain, ctan = D); with MACROC_MAT_UNIFORM the
+// same kernels take D from constant memory and never touch the arrays.
+//
+// Scatter without colouring or atomics:
+//  * residual: pass 1 writes the 24 element forces to a scratch array that is
+//    SoA over elements (coalesced), pass 2 lets every owned node add its <= 8
+//    contributions in increasing element order;
+//  * Jacobian: one CTA per 32-node operator tile, warp a = local node a of the
+//    element, lane = node.  Thread (a, lane) integrates the 3x24 row block of
+//    "its" element (the one in which the node is local node a) in registers --
+//    no flop is done twice -- then the 8 warps add their blocks into the tile in
+//    shared memory in 8 conflict-free rounds (round b: block column b; within a
+//    round distinct a hit distinct stencil slots), the Dirichlet mask is applied
+//    and the tile leaves as one contiguous 62 KB store.
+#pragma once
+
+#include "kernels.cuh"
+
+namespace macroc {
+
+struct ElemRange {
+    int ezs;          // first element layer stored (global z index)
+    int nez_ext;      // stored layers: owned ones plus the upper neighbour's first layer
+    int64_t nex, ney; // elements per row / rows per layer
+};
+
+// MicroPP stand-in on the device: sigma = D eps, C = D for every Gauss point.
+__global__ void k_homogenize_linear(int64_t ngp, const double *__restrict__ strain, double *__restrict__ stress,
+                                    double *__restrict__ ctan)
+{
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < ngp * 6) {
+        int64_t gpi = t / 6; int i = (int)(t % 6);
+        double s = 0.;
+#pragma unroll
+        for (int j = 0; j < 6; ++j) s = fma(c_D[i * 6 + j], strain[gpi * 6 + j], s);
+        stress[t] = s;
+    }
+    if (ctan)
+        for (int64_t q = t; q < ngp * 36; q += (int64_t)gridDim.x * blockDim.x) ctan[q] = c_D[q % 36];
+}
+
+// pass 1: be[24] of every stored element in layers [l0, l0+nl) of the range -> scratch[q][e_local]
+template <bool PER_GP>
+__global__ void __launch_bounds__(128)
+k_elem_forces(GridDev g, ElemRange er, int l0, int nl, double wg, const double *__restrict__ u,
+              const double *__restrict__ stress_gp, double *__restrict__ scratch)
+{
+    const int64_t per_layer = er.nex * er.ney, n = per_layer * nl;
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    int ei = (int)(e % er.nex), ej = (int)((e / er.nex) % er.ney), el = (int)(e / per_layer) + l0;
+    double be[24];
+#pragma unroll
+    for (int q = 0; q < 24; ++q) be[q] = 0.;
+    double ue[8][3];
+    if (!PER_GP) gather_element(u, g, g.G + ei + (int64_t)g.NX * ej + g.npl * (er.ezs + el - g.zs), ue);
+    const double *sg = PER_GP ? stress_gp + ((int64_t)el * per_layer + (e % per_layer)) * 48 : nullptr;
+#pragma unroll 1
+    for (int gp = 0; gp < 8; ++gp) {
+        double sig[6];
+        if (PER_GP) {
+#pragma unroll
+            for (int q = 0; q < 6; ++q) sig[q] = __ldg(sg + gp * 6 + q);
+        } else {
+            double eps[6];
+            element_strain(ue, gp, eps);
+            stress_of(eps, sig);
+        }
+#pragma unroll
+        for (int a = 0; a < 8; ++a) {
+            const double hx = c_dsh[gp][a][0], hy = c_dsh[gp][a][1], hz = c_dsh[gp][a][2];
+            // be[i] += B[j][i]*stress[j]*wg, j ascending (assembly.c:151-153)
+            be[3 * a + 0] += hx * sig[0] * wg; be[3 * a + 0] += hy * sig[3] * wg; be[3 * a + 0] += hz * sig[4] * wg;
+            be[3 * a + 1] += hy * sig[1] * wg; be[3 * a + 1] += hx * sig[3] * wg; be[3 * a + 1] += hz * sig[5] * wg;
+            be[3 * a + 2] += hz * sig[2] * wg; be[3 * a + 2] += hx * sig[4] * wg; be[3 * a + 2] += hy * sig[5] * wg;
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 24; ++q) scratch[q * n + e] = be[q];
+}
+
+// pass 2: nodes of planes [k0, k0+nk) (slab-local) add their element forces, apply the
+// Dirichlet mask and the sign (bcs.c:350-362, assembly.c:173) and accumulate |b|^2.
+__global__ void __launch_bounds__(256)
+k_gather_forces(GridDev g, ElemRange er, int l0, int nl, int k0, int nk, const double *__restrict__ scratch,
+                const uint8_t *__restrict__ nodemask, double *__restrict__ b, double *__restrict__ partial)
+{
+    __shared__ double sm[8];
+    const int64_t per_layer = er.nex * er.ney, n = per_layer * nl;
+    int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    double sq = 0.;
+    if (q < g.npl * nk) {
+        int64_t ln = (int64_t)k0 * g.npl + q;
+        int i = (int)(ln % g.NX), j = (int)((ln / g.NX) % g.NY), k = (int)(ln / g.npl) + g.zs;
+        double r0 = 0., r1 = 0., r2 = 0.;
+        for (int oz = -1; oz <= 0; ++oz)
+            for (int oy = -1; oy <= 0; ++oy)
+                for (int ox = -1; ox <= 0; ++ox) {
+                    int ei = i + ox, ej = j + oy, ek = k + oz;
+                    if (ei < 0 || ei >= g.NX - 1 || ej < 0 || ej >= g.NY - 1 || ek < 0 || ek >= g.NZ - 1) continue;
+                    int el = ek - er.ezs - l0;                  // layer inside the scratch chunk
+                    if (el < 0 || el >= nl) continue;           // (cannot happen for a correct chunking)
+                    int a = local_node_of_pos(-ox, -oy, -oz);
+                    int64_t e = ei + er.nex * (ej + er.ney * (int64_t)el);
+                    r0 += scratch[(3 * a + 0) * n + e];
+                    r1 += scratch[(3 * a + 1) * n + e];
+                    r2 += scratch[(3 * a + 2) * n + e];
+                }
+        unsigned own = nodemask[g.G + ln];
+        r0 = (own & 1u) ? 0. : -r0;
+        r1 = (own & 2u) ? 0. : -r1;
+        r2 = (own & 4u) ? 0. : -r2;
+        double *b0 = b + g.G + ln;
+        b0[0] = r0; b0[g.S] = r1; b0[2 * g.S] = r2;
+        sq = r0 * r0 + r1 * r1 + r2 * r2;
+    }
+    double s = block_sum<8>(sq, sm);
+    if (threadIdx.x == 0) partial[blockIdx.x] = s;
+}
+
+// General Jacobian assembly, one CTA (8 warps) per operator tile.
+template <bool PER_GP>
+__global__ void __launch_bounds__(256)
+k_assemble_elements(GridDev g, ElemRange er, double wg, const double *__restrict__ ctan_gp,
+                    const uint8_t *__restrict__ nodemask, double2 *__restrict__ A, double *__restrict__ dinv)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *tileA = reinterpret_cast<double *>(smem_raw);                  // TILE_DOUBLES
+    uint8_t *nbmask = smem_raw + TILE_DOUBLES * sizeof(double);            // [27][32]
+    const int lane = threadIdx.x & 31, a = threadIdx.x >> 5;
+    const int apx = node_px(a), apy = node_py(a), apz = node_pz(a);
+    const int64_t per_layer = er.nex * er.ney;
+
+    for (int64_t tile = blockIdx.x; tile < g.ntiles; tile += gridDim.x) {
+        const int64_t ln = tile * TILE_NODES + lane;
+        const bool valid = ln < g.nloc;
+        int i = 0, j = 0, k = 0;
+        if (valid) { i = (int)(ln % g.NX); j = (int)((ln / g.NX) % g.NY); k = (int)(ln / g.npl) + g.zs; }
+        for (int q = threadIdx.x; q < TILE_DOUBLES; q += blockDim.x) tileA[q] = 0.;
+        for (int q = threadIdx.x; q < 27 * 32; q += blockDim.x) {
+            int slot = q >> 5, l2 = q & 31;
+            int64_t ln2 = tile * TILE_NODES + l2;
+            const int ddx = slot % 3 - 1, ddy = (slot / 3) % 3 - 1, ddz = slot / 9 - 1;
+            nbmask[q] = ln2 < g.nloc ? nodemask[g.G + ln2 + ddx + (int64_t)g.NX * ddy + g.npl * ddz] : 0;
+        }
+        // the element in which this node is local node a
+        const int ei = i - apx, ej = j - apy, ek = k - apz;
+        const bool exists = valid && ei >= 0 && ei < g.NX - 1 && ej >= 0 && ej < g.NY - 1 && ek >= 0 && ek < g.NZ - 1;
+        double blk[3][24];
+#pragma unroll
+        for (int d = 0; d < 3; ++d)
+#pragma unroll
+            for (int q = 0; q < 24; ++q) blk[d][q] = 0.;
+        if (exists) {
+            const double *cg = PER_GP ? ctan_gp + ((int64_t)(ek - er.ezs) * per_layer + ei + er.nex * (int64_t)ej) * 288 : nullptr;
+#pragma unroll 1
+            for (int gp = 0; gp < 8; ++gp) {
+                double C[36];
+#pragma unroll
+                for (int q = 0; q < 36; ++q) C[q] = PER_GP ? __ldg(cg + gp * 36 + q) : c_D[q];
+                const double hx = c_dsh[gp][a][0], hy = c_dsh[gp][a][1], hz = c_dsh[gp][a][2];
+                double T[3][6];                         // rows 3a..3a+2 of B^T C
+#pragma unroll
+                for (int l = 0; l < 6; ++l) {
+                    T[0][l] = hx * C[0 * 6 + l] + hy * C[3 * 6 + l] + hz * C[4 * 6 + l];
+                    T[1][l] = hy * C[1 * 6 + l] + hx * C[3 * 6 + l] + hz * C[5 * 6 + l];
+                    T[2][l] = hz * C[2 * 6 + l] + hx * C[4 * 6 + l] + hy * C[5 * 6 + l];
+                }
+#pragma unroll
+                for (int b = 0; b < 8; ++b) {
+                    const double bx = c_dsh[gp][b][0] * wg, by = c_dsh[gp][b][1] * wg, bz = c_dsh[gp][b][2] * wg;
+#pragma unroll
+                    for (int d = 0; d < 3; ++d) {
+                        blk[d][3 * b + 0] += T[d][0] * bx + T[d][3] * by + T[d][4] * bz;
+                        blk[d][3 * b + 1] += T[d][1] * by + T[d][3] * bx + T[d][5] * bz;
+                        blk[d][3 * b + 2] += T[d][2] * bz + T[d][4] * bx + T[d][5] * by;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        // 8 rounds: in round b every warp adds block column b; for a fixed b the 8 warps
+        // (different a) target 8 different slots, so no two threads touch the same entry
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+            if (exists) {
+                const int slot = (node_pz(b) - apz + 1) * 9 + (node_py(b) - apy + 1) * 3 + (node_px(b) - apx + 1);
+#pragma unroll
+                for (int d = 0; d < 3; ++d)
+#pragma unroll
+                    for (int cc = 0; cc < 3; ++cc) {
+                        const int kk = slot * 9 + 3 * d + cc;
+                        tileA[((kk >> 1) * TILE_NODES + lane) * 2 + (kk & 1)] += blk[d][3 * b + cc];
+                    }
+            }
+            __syncthreads();
+        }
+        // MatZeroRowsColumns (bcs.c:341-347) + PCJACOBI diagonal + coalesced store
+        double2 *At = A + tile * (PAIRS * TILE_NODES);
+        for (int q = threadIdx.x; q < PAIRS * TILE_NODES; q += blockDim.x) {
+            const int l2 = q & 31, pr = q >> 5;
+            const unsigned own = nbmask[13 * 32 + l2];
+            double v2[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int kk = 2 * pr + h;
+                double v = tileA[2 * q + h];
+                if (kk < ENTRIES) {
+                    const int slot = kk / 9, rr = (kk % 9) / 3, cc = kk % 3;
+                    const unsigned nb = nbmask[slot * 32 + l2];
+                    if (((own >> rr) & 1u) || ((nb >> cc) & 1u)) v = (slot == 13 && rr == cc) ? 1. : 0.;
+                    if (slot == 13 && rr == cc && tile * TILE_NODES + l2 < g.nloc)
+                        dinv[rr * g.S + g.G + tile * TILE_NODES + l2] = v != 0. ? 1. / v : 1.;
+                } else
+                    v = 0.;
+                v2[h] = v;
+            }
+            At[q] = make_double2(v2[0], v2[1]);
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace macroc

@@ -21,6 +21,7 @@
 #include "grid.h"
 #include "kernels.cuh"
 #include "spmv_tma.cuh"
+#include "assembly_elem.cuh"
 
 using namespace macroc;
 
@@ -52,7 +53,11 @@ struct macroc_ctx {
     CgScalars *sc = nullptr;         // device
     CgScalars *sc_host = nullptr;    // pinned [2]
     double *stage = nullptr;         // device staging, 3*nloc doubles (boundary layout)
-    double *strain = nullptr, *stress = nullptr;
+    double *strain = nullptr, *stress = nullptr, *ctan = nullptr;   // Gauss-point arrays, gpi = ie*8+gp
+    double *scratch = nullptr;       // element forces of one z-chunk, SoA over elements
+    int chunk_planes = 0;
+    ElemRange er;
+    int64_t ne_owned = 0, ne_ext = 0;
     double *flush = nullptr;
     size_t flush_bytes = 0;
     uint64_t launches = 0;
@@ -235,6 +240,7 @@ static int ctx_free(macroc_ctx *c)
     for (int i = 0; i < V_COUNT; ++i) cudaFree(c->vec[i]);
     cudaFree(c->A); cudaFree(c->Ke); cudaFree(c->T); cudaFree(c->nodemask); cudaFree(c->bc_idx); cudaFree(c->bc_coef);
     cudaFree(c->partial); cudaFree(c->sums); cudaFree(c->sc); cudaFree(c->stage); cudaFree(c->strain); cudaFree(c->stress);
+    cudaFree(c->ctan); cudaFree(c->scratch);
     cudaFree(c->flush);
     if (c->sums_host) cudaFreeHost(c->sums_host);
     if (c->sc_host) cudaFreeHost(c->sc_host);
@@ -298,9 +304,23 @@ extern "C" int macroc_create(const macroc_config *cfg, int rank, int nranks, con
     CUC(cudaMalloc(&c->stage, sizeof(double) * 3 * (size_t)g.nloc));
     c->vec_blocks = std::min<int64_t>(cdiv64(g.nloc, 256), 148 * 8);
     c->spmv_blocks = std::min<int64_t>(cdiv64(g.ntiles, 8), 148 * 8);
-    c->partial_cap = std::max<int64_t>({(int64_t)cdiv64(g.nloc, 128), (int64_t)2 * c->vec_blocks, (int64_t)3 * c->spmv_blocks + 8, (int64_t)4096});
+    c->partial_cap = std::max<int64_t>({(int64_t)cdiv64(g.nloc, 128) + slab.nzl + 8, (int64_t)2 * c->vec_blocks, (int64_t)3 * c->spmv_blocks + 8, (int64_t)4096});
     CUC(cudaMalloc(&c->partial, sizeof(double) * c->partial_cap));
 
+    // element bookkeeping: DMDA-owned layers plus, for the gather-form assembly, the first layer
+    // of the upper neighbour (integrated redundantly / received as Gauss-point halo)
+    c->er.ezs = slab.ezs; c->er.nex = slab.nex; c->er.ney = slab.ney;
+    c->er.nez_ext = slab.nez + (slab.has_upper() ? 1 : 0);
+    c->ne_owned = (int64_t)slab.nex * slab.ney * slab.nez;
+    c->ne_ext = (int64_t)slab.nex * slab.ney * c->er.nez_ext;
+    {
+        // residual scratch: 24 doubles per element of a chunk of node planes (<= ~256 MB)
+        int64_t per_layer = std::max<int64_t>((int64_t)slab.nex * slab.ney, 1);
+        int64_t max_layers = std::max<int64_t>(2, ((int64_t)256 << 20) / (per_layer * 24 * 8));
+        c->chunk_planes = (int)std::min<int64_t>(slab.nzl, max_layers - 1);
+        if (c->chunk_planes < 1) c->chunk_planes = 1;
+        CUC(cudaMalloc(&c->scratch, sizeof(double) * 24 * per_layer * (c->chunk_planes + 1)));
+    }
     // Dirichlet bookkeeping: the reference's lists (bc_init) -> per-node dof mask
     // over the padded slab (ghost planes included) + owned (index, coef) pairs.
     {
@@ -408,22 +428,124 @@ extern "C" int macroc_apply_bc_on_u(macroc_ctx *c, double U)
     return MACROC_OK;
 }
 
+static int ensure_gp_arrays(macroc_ctx *c, bool need_ctan)
+{
+    size_t n = (size_t)std::max<int64_t>(c->ne_ext, 1);
+    if (!c->strain) {
+        CU(c, cudaMalloc(&c->strain, sizeof(double) * 48 * n));
+        CU(c, cudaMalloc(&c->stress, sizeof(double) * 48 * n));
+        CU(c, cudaMemsetAsync(c->strain, 0, sizeof(double) * 48 * n, c->stream));
+        CU(c, cudaMemsetAsync(c->stress, 0, sizeof(double) * 48 * n, c->stream));
+    }
+    if (need_ctan && !c->ctan) {
+        cudaError_t e = cudaMalloc(&c->ctan, sizeof(double) * 288 * n);
+        if (e != cudaSuccess) { cudaGetLastError(); FAIL(c, MACROC_ERR_MEM, "per-Gauss-point tangents need %.2f GB", 288. * 8 * n / 1e9); }
+        CU(c, cudaMemsetAsync(c->ctan, 0, sizeof(double) * 288 * n, c->stream));
+    }
+    return MACROC_OK;
+}
+
+// Gauss-point halo: the first owned element layer of rank r+1 is the layer above rank r's
+// top node plane; rank r keeps a copy behind its owned layers (layer index nez).
+static int halo_gp_layer(macroc_ctx *c, double *arr, int doubles_per_elem)
+{
+    if (!c->comm) return MACROC_OK;
+    const Slab &s = c->slab;
+    size_t cnt = (size_t)s.nex * s.ney * doubles_per_elem;
+    NC(c, ncclGroupStart());
+    if (s.has_lower()) NC(c, ncclSend(arr, cnt, ncclDouble, s.rank - 1, c->comm, c->stream));
+    if (s.has_upper()) NC(c, ncclRecv(arr + (size_t)c->ne_owned * doubles_per_elem, cnt, ncclDouble, s.rank + 1, c->comm, c->stream));
+    NC(c, ncclGroupEnd());
+    return MACROC_OK;
+}
+
 extern "C" int macroc_set_strains(macroc_ctx *c, int materialize)
 {
     if (!c) return MACROC_ERR_ARG;
     CU(c, cudaSetDevice(c->device));
     int rc = halo_exchange(c, c->vec[V_U], c->stream);
     if (rc) return rc;
-    if (materialize) {
+    if (materialize || c->cfg.material == MACROC_MAT_PER_GP) {
         const Slab &s = c->slab;
-        int64_t ne = (int64_t)s.nex * s.ney * s.nez;
-        if (!c->strain && ne > 0) {
-            CU(c, cudaMalloc(&c->strain, sizeof(double) * 48 * (size_t)ne));
-            CU(c, cudaMalloc(&c->stress, sizeof(double) * 48 * (size_t)ne));
-        }
-        if (ne > 0) LAUNCH(c, k_strain_stress, cdiv64(ne, 128), 128, c->g, s.ezs, s.nez, c->vec[V_U], c->strain, c->stress);
+        if ((rc = ensure_gp_arrays(c, false))) return rc;
+        // strain of the owned elements; stress = D strain as a by-product for the uniform law
+        if (c->ne_owned > 0)
+            LAUNCH(c, k_strain_stress, cdiv64(c->ne_owned, 128), 128, c->g, s.ezs, s.nez, c->vec[V_U], c->strain,
+                   c->cfg.material == MACROC_MAT_PER_GP ? nullptr : c->stress);
         CU(c, cudaGetLastError());
     }
+    return MACROC_OK;
+}
+
+extern "C" int macroc_homogenize(macroc_ctx *c)
+{
+    if (!c) return MACROC_ERR_ARG;
+    if (c->cfg.material != MACROC_MAT_PER_GP) return MACROC_OK;
+    CU(c, cudaSetDevice(c->device));
+    int rc = ensure_gp_arrays(c, true);
+    if (rc) return rc;
+    int64_t ngp = c->ne_owned * 8;
+    if (ngp > 0) LAUNCH(c, k_homogenize_linear, (int)std::min<int64_t>(cdiv64(ngp * 6, 256), 148 * 16), 256, ngp, c->strain, c->stress, c->ctan);
+    // grid-stride part covers ctan; the stress part needs one thread per value
+    if (ngp * 6 > (int64_t)148 * 16 * 256)
+        LAUNCH(c, k_homogenize_linear, cdiv64(ngp * 6, 256), 256, ngp, c->strain, c->stress, (double *)nullptr);
+    CU(c, cudaGetLastError());
+    return MACROC_OK;
+}
+
+extern "C" int macroc_gp_arrays(macroc_ctx *c, double **strain, double **stress, double **ctan, int64_t *n_gp)
+{
+    if (!c) return MACROC_ERR_ARG;
+    CU(c, cudaSetDevice(c->device));
+    int rc = ensure_gp_arrays(c, ctan != nullptr);
+    if (rc) return rc;
+    if (strain) *strain = c->strain;
+    if (stress) *stress = c->stress;
+    if (ctan) *ctan = c->ctan;
+    if (n_gp) *n_gp = c->ne_owned * 8;
+    return MACROC_OK;
+}
+
+extern "C" int macroc_set_gp_data(macroc_ctx *c, const double *stress_host, const double *ctan_host)
+{
+    if (!c) return MACROC_ERR_ARG;
+    CU(c, cudaSetDevice(c->device));
+    int rc = ensure_gp_arrays(c, ctan_host != nullptr);
+    if (rc) return rc;
+    if (stress_host && c->ne_owned) CU(c, cudaMemcpyAsync(c->stress, stress_host, sizeof(double) * 48 * c->ne_owned, cudaMemcpyHostToDevice, c->stream));
+    if (ctan_host && c->ne_owned) CU(c, cudaMemcpyAsync(c->ctan, ctan_host, sizeof(double) * 288 * c->ne_owned, cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    return MACROC_OK;
+}
+
+// b = -(sum_e B^T sigma wg) on the owned nodes, two passes per chunk of node planes
+static int residual_launch(macroc_ctx *c, int *nparts_out)
+{
+    const GridDev &g = c->g;
+    const Slab &s = c->slab;
+    const bool per_gp = c->cfg.material == MACROC_MAT_PER_GP;
+    if (per_gp) {
+        if (!c->stress) FAIL(c, MACROC_ERR_ARG, "assembly_res: no Gauss-point stresses (call set_strains + homogenize)");
+        int rc = halo_gp_layer(c, c->stress, 48);
+        if (rc) return rc;
+    }
+    int nparts = 0;
+    const int last_stored = c->er.ezs + c->er.nez_ext - 1;
+    for (int k0 = 0; k0 < s.nzl; k0 += c->chunk_planes) {
+        const int nk = std::min(c->chunk_planes, s.nzl - k0);
+        const int lay_lo = std::max(s.zs + k0 - 1, c->er.ezs), lay_hi = std::min(s.zs + k0 + nk - 1, last_stored);
+        const int l0 = lay_lo - c->er.ezs, nl = lay_hi - lay_lo + 1;
+        if (nl > 0) {
+            int64_t n = (int64_t)s.nex * s.ney * nl;
+            if (per_gp) LAUNCH(c, k_elem_forces<true>, cdiv64(n, 128), 128, g, c->er, l0, nl, c->geo.wg, c->vec[V_U], c->stress, c->scratch);
+            else LAUNCH(c, k_elem_forces<false>, cdiv64(n, 128), 128, g, c->er, l0, nl, c->geo.wg, c->vec[V_U], c->stress, c->scratch);
+        }
+        int blocks = cdiv64(g.npl * nk, 256);
+        LAUNCH(c, k_gather_forces, blocks, 256, g, c->er, l0, std::max(nl, 0), k0, nk, c->scratch, c->nodemask, c->vec[V_B], c->partial + nparts);
+        nparts += blocks;
+    }
+    *nparts_out = nparts;
+    CU(c, cudaGetLastError());
     return MACROC_OK;
 }
 
@@ -431,10 +553,11 @@ extern "C" int macroc_assembly_res(macroc_ctx *c, double *norm)
 {
     if (!c) return MACROC_ERR_ARG;
     CU(c, cudaSetDevice(c->device));
-    int nblk = cdiv64(c->g.nloc, 128);
-    LAUNCH(c, k_residual, nblk, 128, c->g, c->geo.wg, c->vec[V_U], c->nodemask, c->vec[V_B], c->partial);
-    LAUNCH(c, k_reduce, 1, 256, c->partial, nblk, c->sums);
-    int rc = allreduce_sums(c, 1);
+    int nparts = 0;
+    int rc = residual_launch(c, &nparts);
+    if (rc) return rc;
+    LAUNCH(c, k_reduce, 1, 256, c->partial, nparts, c->sums);
+    rc = allreduce_sums(c, 1);
     if (rc) return rc;
     CU(c, cudaMemcpyAsync(c->sums_host, c->sums, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
@@ -459,12 +582,31 @@ extern "C" int macroc_assembly_jac(macroc_ctx *c)
     if (!c) return MACROC_ERR_ARG;
     CU(c, cudaSetDevice(c->device));
     if (c->cfg.op == MACROC_OP_MATRIX_FREE) {
+        if (c->cfg.material != MACROC_MAT_UNIFORM) FAIL(c, MACROC_ERR_UNSUPPORTED, "matrix-free operator needs the uniform tangent");
         LAUNCH(c, k_mf_diag, cdiv64(c->g.nloc, 256), 256, c->g, c->T, c->nodemask, c->vec[V_DINV]);
         c->mf_ready = true;
     } else {
         int rc = ensure_operator_storage(c);
         if (rc) return rc;
-        LAUNCH(c, k_fill_operator, cdiv64(c->g.ntiles, 8), 256, c->g, c->T, c->nodemask, c->A, c->vec[V_DINV]);
+        const bool per_gp = c->cfg.material == MACROC_MAT_PER_GP;
+        if (per_gp || c->cfg.jac_mode == MACROC_JAC_ELEMENT) {
+            if (per_gp) {
+                if (!c->ctan) FAIL(c, MACROC_ERR_ARG, "assembly_jac: no Gauss-point tangents (call homogenize)");
+                if ((rc = halo_gp_layer(c, c->ctan, 288))) return rc;
+            }
+            const int smem = TILE_DOUBLES * (int)sizeof(double) + 27 * 32;
+            static bool configured = false;
+            if (!configured) {
+                cudaFuncSetAttribute(k_assemble_elements<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+                cudaFuncSetAttribute(k_assemble_elements<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+                configured = true;
+            }
+            int blocks = (int)std::min<int64_t>(c->g.ntiles, 148 * 3);
+            if (per_gp) k_assemble_elements<true><<<blocks, 256, smem, c->stream>>>(c->g, c->er, c->geo.wg, c->ctan, c->nodemask, c->A, c->vec[V_DINV]);
+            else k_assemble_elements<false><<<blocks, 256, smem, c->stream>>>(c->g, c->er, c->geo.wg, c->ctan, c->nodemask, c->A, c->vec[V_DINV]);
+            c->launches++;
+        } else
+            LAUNCH(c, k_fill_operator, cdiv64(c->g.ntiles, 8), 256, c->g, c->T, c->nodemask, c->A, c->vec[V_DINV]);
         c->A_valid = true;
     }
     CU(c, cudaGetLastError());
@@ -520,7 +662,8 @@ static int spmv_launch(macroc_ctx *c, double *p, double *w, int64_t first, int64
 
 // w = A p on the context's stream; p's halo is exchanged on comm_stream while
 // the rows that do not touch a ghost plane are computed.
-static int apply_operator(macroc_ctx *c, int op, double *p, double *w, bool with_dot, const int *done)
+static int apply_operator(macroc_ctx *c, int op, double *p, double *w, bool with_dot, const int *done,
+                          bool fuse_pw_scalars = false)
 {
     const GridDev &g = c->g;
     const bool comm = c->comm != nullptr;
@@ -565,7 +708,10 @@ static int apply_operator(macroc_ctx *c, int op, double *p, double *w, bool with
         run(hi_begin, total - hi_begin);
     } else
         run(0, total);
-    if (with_dot) LAUNCH(c, k_reduce, 1, 256, c->partial, nparts, c->sums);
+    if (with_dot) {
+        if (fuse_pw_scalars) LAUNCH(c, k_cg_reduce_pw, 1, 256, c->partial, nparts, c->sc);
+        else LAUNCH(c, k_reduce, 1, 256, c->partial, nparts, c->sums);
+    }
     CU(c, cudaGetLastError());
     return MACROC_OK;
 }
@@ -577,17 +723,24 @@ static int cg_iteration(macroc_ctx *c, int op)
     LAUNCH(c, k_cg_update_p, nb, 256, g, c->sc, c->vec[V_R], c->vec[V_DINV], c->vec[V_P]);
     const bool sample = c->prof_on && c->prof_used < macroc_ctx::PROF_RING && (c->prof_counter++ % c->prof_stride) == 0;
     if (sample) CU(c, cudaEventRecord(c->prof_ev[2 * c->prof_used], c->stream));
-    int rc = apply_operator(c, op, c->vec[V_P], c->vec[V_W], true, &c->sc->done);
+    const bool single = c->comm == nullptr;      // no all-reduce between reduction and scalar update
+    int rc = apply_operator(c, op, c->vec[V_P], c->vec[V_W], true, &c->sc->done, single);
     if (rc) return rc;
     if (sample) { CU(c, cudaEventRecord(c->prof_ev[2 * c->prof_used + 1], c->stream)); c->prof_used++; }
-    rc = allreduce_sums(c, 1);
-    if (rc) return rc;
-    LAUNCH(c, k_cg_scalars_pw, 1, 1, c->sc, c->sums);
+    if (!single) {
+        rc = allreduce_sums(c, 1);
+        if (rc) return rc;
+        LAUNCH(c, k_cg_scalars_pw, 1, 1, c->sc, c->sums);
+    }
     LAUNCH(c, k_cg_update_xr, nb, 256, g, c->sc, c->vec[V_P], c->vec[V_W], c->vec[V_DINV], c->vec[V_DU], c->vec[V_R], c->partial, nb);
-    LAUNCH(c, k_reduce2, 1, 256, c->partial, nb, c->sums);
-    rc = allreduce_sums(c, 2);
-    if (rc) return rc;
-    LAUNCH(c, k_cg_scalars_iter, 1, 1, c->sc, c->sums);
+    if (single) {
+        LAUNCH(c, k_cg_reduce_iter, 1, 256, c->partial, nb, c->sc);
+    } else {
+        LAUNCH(c, k_reduce2, 1, 256, c->partial, nb, c->sums);
+        rc = allreduce_sums(c, 2);
+        if (rc) return rc;
+        LAUNCH(c, k_cg_scalars_iter, 1, 1, c->sc, c->sums);
+    }
     return MACROC_OK;
 }
 
@@ -708,6 +861,7 @@ extern "C" int macroc_time_step(macroc_ctx *c, int time_s, int *newton_its, doub
     double norm = 0., norm_0 = 0.;
     while (newton_it < c->cfg.newton_max_its) {
         if ((rc = macroc_set_strains(c, 0))) return rc;
+        if ((rc = macroc_homogenize(c))) return rc;                  /* main.c:62 */
         if ((rc = macroc_assembly_res(c, &norm))) return rc;
         if (res_norms) res_norms[nres] = norm;
         nres++;
@@ -808,7 +962,7 @@ extern "C" int macroc_get_strain_stress(macroc_ctx *c, double *strain, double *s
 {
     if (!c) return MACROC_ERR_ARG;
     CU(c, cudaSetDevice(c->device));
-    int64_t ne = (int64_t)c->slab.nex * c->slab.ney * c->slab.nez;
+    int64_t ne = c->ne_owned;
     if (n_gp) *n_gp = ne * 8;
     if ((strain || stress) && !c->strain && ne > 0) FAIL(c, MACROC_ERR_ARG, "get_strain_stress: call set_strains(ctx, 1) first");
     if (strain && ne > 0) CU(c, cudaMemcpyAsync(strain, c->strain, sizeof(double) * 48 * ne, cudaMemcpyDeviceToHost, c->stream));
@@ -906,6 +1060,12 @@ extern "C" int macroc_time_kernel(macroc_ctx *c, int what, int reps, int flush_l
                 break;
             }
             case 4: {
+                int nparts = 0;
+                rc = residual_launch(c, &nparts);
+                if (!rc) LAUNCH(c, k_reduce, 1, 256, c->partial, nparts, c->sums);
+                break;
+            }
+            case 6: {                                   // legacy node-gather residual, for comparison
                 int nblk = cdiv64(g.nloc, 128);
                 LAUNCH(c, k_residual, nblk, 128, g, c->geo.wg, c->vec[V_U], c->nodemask, c->vec[V_B], c->partial);
                 LAUNCH(c, k_reduce, 1, 256, c->partial, nblk, c->sums);

@@ -453,7 +453,7 @@ k_strain_stress(GridDev g, int ezs, int nez, const double *__restrict__ u, doubl
 #pragma unroll
         for (int q = 0; q < 6; ++q) {
             strain[(ie * 8 + gp) * 6 + q] = eps[q];
-            stress[(ie * 8 + gp) * 6 + q] = sig[q];
+            if (stress) stress[(ie * 8 + gp) * 6 + q] = sig[q];
         }
     }
 }
@@ -656,27 +656,59 @@ k_cg_update_xr(GridDev g, const CgScalars *__restrict__ s, const double *__restr
     if (threadIdx.x == 0) { partial[blockIdx.x] = s0; partial[nblk + blockIdx.x] = s1; }
 }
 
+__device__ __forceinline__ void cg_scalars_pw_body(CgScalars *s, double pw)
+{
+    s->pw = pw;
+    s->its += 1;                               // ksp->its = i+1 at the top of the loop body
+    if (pw == 0.) { s->done = 1; s->reason = -10; }
+}
+
+__device__ __forceinline__ void cg_scalars_iter_body(CgScalars *s, double zz, double zr)
+{
+    double dp = sqrt(zz);
+    s->dp = dp;
+    if (dp <= s->ttol) { s->done = 1; s->reason = dp <= s->abstol ? 3 : 2; return; }
+    if (dp >= s->dtol * s->dp0) { s->done = 1; s->reason = -4; return; }
+    if (s->its >= s->maxits) { s->done = 1; s->reason = -3; return; }
+    s->betaold = s->beta;
+    s->beta = zr;
+    if (s->beta == 0.) { s->its += 1; s->done = 1; s->reason = 3; }   // KSP_CONVERGED_ATOL at the next top
+}
+
 // after the p.w reduction: store it (and flag an indefinite matrix)
 __global__ void k_cg_scalars_pw(CgScalars *s, const double *sum)
 {
     if (s->done) return;
-    s->pw = sum[0];
-    s->its += 1;                               // ksp->its = i+1 at the top of the loop body
-    if (s->pw == 0.) { s->done = 1; s->reason = -10; }
+    cg_scalars_pw_body(s, sum[0]);
 }
 
 // after the (z.z, z.r) reduction: convergence test and beta rotation
 __global__ void k_cg_scalars_iter(CgScalars *s, const double *sums)
 {
     if (s->done) return;
-    double dp = sqrt(sums[0]);
-    s->dp = dp;
-    if (dp <= s->ttol) { s->done = 1; s->reason = dp <= s->abstol ? 3 : 2; return; }
-    if (dp >= s->dtol * s->dp0) { s->done = 1; s->reason = -4; return; }
-    if (s->its >= s->maxits) { s->done = 1; s->reason = -3; return; }
-    s->betaold = s->beta;
-    s->beta = sums[1];
-    if (s->beta == 0.) { s->its += 1; s->done = 1; s->reason = 3; }   // KSP_CONVERGED_ATOL at the next top
+    cg_scalars_iter_body(s, sums[0], sums[1]);
+}
+
+// single-rank fast path: partial reduction and scalar update in one launch
+__global__ void k_cg_reduce_pw(const double *__restrict__ partial, int nblk, CgScalars *s)
+{
+    __shared__ double sm[8];
+    if (s->done) return;
+    double v = 0.;
+    for (int q = threadIdx.x; q < nblk; q += blockDim.x) v += partial[q];
+    v = block_sum<8>(v, sm);
+    if (threadIdx.x == 0) cg_scalars_pw_body(s, v);
+}
+
+__global__ void k_cg_reduce_iter(const double *__restrict__ partial, int nblk, CgScalars *s)
+{
+    __shared__ double sm[8];
+    if (s->done) return;
+    double s0 = 0., s1 = 0.;
+    for (int q = threadIdx.x; q < nblk; q += blockDim.x) { s0 += partial[q]; s1 += partial[nblk + q]; }
+    s0 = block_sum<8>(s0, sm);
+    s1 = block_sum<8>(s1, sm);
+    if (threadIdx.x == 0) cg_scalars_iter_body(s, s0, s1);
 }
 
 // reduce two partial arrays at once: out[0], out[1]

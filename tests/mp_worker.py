@@ -83,11 +83,13 @@ def gpu_mode(args):
              (33, 9, 4 * world + 3, M.BC_BENDING, dict(lx=10., ly=1., lz=1.)),
              (9, 3, max(9, world), M.BC_CIRCLE, dict(lx=4., lz=4.))]
     for (NX, NY, NZ, bc, extra) in cases:
-        for op in (M.OP_ASSEMBLED, M.OP_MATRIX_FREE):
+        for op, material in ((M.OP_ASSEMBLED, M.MAT_UNIFORM), (M.OP_MATRIX_FREE, M.MAT_UNIFORM),
+                             (M.OP_ASSEMBLED, M.MAT_PER_GP)):
             box = [M.get_unique_id() if rank == 0 else None]
             dist.broadcast_object_list(box, src=0)
             ts = 3
-            cfg = M.Config(NX=NX, NY=NY, NZ=NZ, bc_type=bc, pz=world, ts=ts, ksp_rtol=1e-12, op=op, device=local, **extra)
+            cfg = M.Config(NX=NX, NY=NY, NZ=NZ, bc_type=bc, pz=world, ts=ts, ksp_rtol=1e-12, op=op, device=local,
+                           material=material, **extra)
             m = M.MacroC(cfg, rank=rank, nranks=world, unique_id=box[0])
             logs = [m.time_step(t) for t in range(ts)]
             u_loc = m.get_vec(M.VEC_U)
@@ -97,7 +99,7 @@ def gpu_mode(args):
             zs, zm = p["corners"][2], p["corners"][5]
             sl = slice(3 * NX * NY * zs, 3 * NX * NY * (zs + zm))
             if op == M.OP_ASSEMBLED:
-                m.assembly_jac()
+                m.set_strains(); m.homogenize(); m.assembly_jac()
             y_loc = m.matmult(x[sl], op)
             A_loc = m.get_matrix_blocks() if op == M.OP_ASSEMBLED else None
             got = gather_objects((u_loc, y_loc, A_loc, logs, force))
@@ -111,7 +113,10 @@ def gpu_mode(args):
                 assert rel_err(y, o.matmult(x)) < 1e-13
                 if op == M.OP_ASSEMBLED:
                     A = np.concatenate([g[2] for g in got])
-                    assert np.array_equal(A, o.block_stencil())
+                    if material == M.MAT_UNIFORM:
+                        assert np.array_equal(A, o.block_stencil())
+                    else:
+                        assert rel_err(A, o.block_stencil()) < 1e-12
                 for g in got:
                     assert [l["newton_its"] for l in g[3]] == [l.newton_its for l in ologs]
                     assert g[3] == got[0][3]                 # every rank saw the same history

@@ -218,3 +218,73 @@ def test_c_host_driver_log_matches_reference(name, tmp_path):
         first += n_lines
     info = np.loadtxt(tmp_path / "info.dat", ndmin=2)
     assert np.allclose(info[:, 3], z["force"], rtol=1e-4, atol=1e-9)
+
+
+# ---------------------------------------------------------------------------------------------
+# per-element kernels and the Gauss-point plug-in boundary
+# ---------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("NX,NY,NZ,bc,extra", [GRIDS[0], GRIDS[2], GRIDS[6], GRIDS[7], GRIDS[8], GRIDS[10]])
+@pytest.mark.parametrize("material,jac_mode", [(M.MAT_UNIFORM, M.JAC_ELEMENT), (M.MAT_PER_GP, M.JAC_AUTO)])
+def test_element_kernels_match_oracle(NX, NY, NZ, bc, extra, material, jac_mode):
+    o = O.Oracle(O.Config(NX=NX, NY=NY, NZ=NZ, bc_type=bc, faithful_ke=0, **extra))
+    m = M.MacroC(M.Config(NX=NX, NY=NY, NZ=NZ, bc_type=bc, material=material, jac_mode=jac_mode, **extra))
+    u0 = 1e-3 * np.random.default_rng(11).standard_normal(o.ndof)
+    o.set_vec("u", u0); m.set_vec(M.VEC_U, u0)
+    U = o.get_displacement(2)
+    o.apply_bc_on_u(U); m.apply_bc_on_u(U)
+    o.set_strains(); o.homogenize(); m.set_strains(); m.homogenize()
+    n_o = o.assembly_res(); n_m = m.assembly_res()
+    assert rel_err(m.get_vec(M.VEC_B), o.get_vec("b")) < TOL_RES
+    assert n_m == pytest.approx(n_o, rel=1e-12)
+    o.assembly_jac(); m.assembly_jac()
+    assert rel_err(m.get_matrix_blocks(), o.block_stencil()) < TOL_MAT
+    if material == M.MAT_PER_GP:
+        eps, sig = m.get_strain_stress()
+        assert rel_err(eps, o.strain(0)) < 1e-13 and rel_err(sig, o.stress(0)) < 1e-13
+    # and the whole loop
+    o2 = O.Oracle(O.Config(NX=NX, NY=NY, NZ=NZ, bc_type=bc, ts=3, rtol=1e-12, faithful_ke=0, **extra))
+    m2 = M.MacroC(M.Config(NX=NX, NY=NY, NZ=NZ, bc_type=bc, ts=3, ksp_rtol=1e-12, material=material,
+                           jac_mode=jac_mode, **extra))
+    logs = o2.run()
+    for t in range(3):
+        assert m2.time_step(t)["newton_its"] == logs[t].newton_its
+    assert rel_err(m2.get_vec(M.VEC_U), o2.get_vec("u")) < TOL_U
+
+
+def test_heterogeneous_gauss_point_data():
+    """Every Gauss point gets its own SPD tangent and stress (what a GPU material model would
+    write): the assembled operator and residual must equal an element-by-element assembly with
+    the oracle's element routines (reference loops assembly.c:94-99, :151-153)."""
+    import scipy.sparse as sp
+    NX, NY, NZ = 7, 4, 5
+    rng = np.random.default_rng(5)
+    m = M.MacroC(M.Config(NX=NX, NY=NY, NZ=NZ, bc_type=M.BC_BENDING, material=M.MAT_PER_GP))
+    o = O.Oracle(O.Config(NX=NX, NY=NY, NZ=NZ, bc_type=M.BC_BENDING))
+    ne = (NX - 1) * (NY - 1) * (NZ - 1)
+    Q = rng.standard_normal((ne, 8, 6, 6))
+    ctan = 1e6 * (Q @ Q.transpose(0, 1, 3, 2) + 6 * np.eye(6))
+    stress = 1e3 * rng.standard_normal((ne, 8, 6))
+    m.set_strains(); m.set_gp_data(stress=stress, ctan=ctan)
+    wg = o.wg
+    eix = o.elements(0)                          # natural numbering on one rank
+    n = 3 * NX * NY * NZ
+    rows, cols, vals = [], [], []
+    b = np.zeros(n)
+    for e in range(ne):
+        dof = (3 * eix[e][:, None] + np.arange(3)[None, :]).reshape(-1)
+        Ke = O.elem_jac(ctan[e].reshape(8, 36), wg)
+        rows.append(np.repeat(dof, 24)); cols.append(np.tile(dof, 24)); vals.append(Ke.reshape(-1))
+        np.add.at(b, dof, O.elem_res(stress[e], wg))
+    K = sp.coo_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(n, n)).tocsr()
+    mask = o.dirichlet_mask_natural()
+    Mk = sp.diags((~mask).astype(float))
+    A = (Mk @ K @ Mk + sp.diags(mask.astype(float))).tocsr()
+    b = -b; b[mask] = 0
+    norm = m.assembly_res()
+    assert rel_err(m.get_vec(M.VEC_B), b) < TOL_RES and norm == pytest.approx(np.linalg.norm(b), rel=1e-12)
+    m.assembly_jac()
+    A_ref = csr_to_block_stencil(A.indptr, A.indices, A.data, NX, NY, NZ)
+    assert rel_err(m.get_matrix_blocks(), A_ref) < TOL_MAT
+    x = rng.standard_normal(n)
+    assert rel_err(m.matmult(x), A @ x) < 1e-13
