@@ -308,6 +308,22 @@ def run_gpu_arm(args):
     e2e_ms_step = max_over_ranks((time.perf_counter() - t0) * 1e3) / args.steps
     h2d = int(sum_over_ranks(8.0 * nloc)); d2h = int(sum_over_ranks(8.0 * nloc + 8.0 * 2))
 
+    # ---- the matrix-free variant offered alongside (north_star): one more time step ----------
+    mf = None
+    if op == M.OP_ASSEMBLED and not args.no_matrix_free:
+        m.set_operator(M.OP_MATRIX_FREE)
+        m.time_step(step_idx); step_idx += 1               # warm-up
+        barrier()
+        m.event_record(2)
+        r = m.time_step(step_idx); step_idx += 1
+        m.event_record(3)
+        barrier()
+        mf_ms = max_over_ranks(m.event_elapsed_ms(2, 3))
+        mf = {"value": nd / (mf_ms * 1e-3), "unit": UNIT, "ms_per_step": mf_ms, "cg_iterations": sum(r["ksp_its"]),
+              "newton_its": r["newton_its"], "note": "same Newton step with the matrix-free 27-point operator"}
+        m.set_operator(M.OP_ASSEMBLED)
+        m.assembly_jac()
+
     # ---- isolated kernel timings (explain the headline; outside the timed regions) ---------
     kern = {}
     if not args.no_kernels:
@@ -369,7 +385,7 @@ def run_gpu_arm(args):
                    "wall_ms_per_step": wall_ms_step},
         "cg_matmult_gbps": roof.get("achieved") if op == M.OP_ASSEMBLED else None,
         "cg_iteration_dof_per_s": nd * its_step / (ms_step * 1e-3) if its_step else None,
-        "roofline": roof, "cpu_baseline": cpu_obj,
+        "roofline": roof, "cpu_baseline": cpu_obj, "matrix_free": mf,
         "e2e": {"value": nd / (e2e_ms_step * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms_step,
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": total_launches, "clocks": clocks, "kernels_ms": kern,
@@ -399,6 +415,7 @@ def main():
     ap.add_argument("--matrix-free", action="store_true", help="solve with the matrix-free operator")
     ap.add_argument("--cg-its", type=int, default=0, help="(reference arm) CG iterations of one step")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-matrix-free", action="store_true", help="skip the extra matrix-free time steps")
     ap.add_argument("--no-kernels", action="store_true", help="skip the isolated kernel timings")
     args = ap.parse_args()
     if args.impl == "reference":

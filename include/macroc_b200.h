@@ -127,6 +127,9 @@ int macroc_assembly_res(macroc_ctx *ctx, double *norm);    /* assembly.c:120-176
 int macroc_assembly_jac(macroc_ctx *ctx);                  /* assembly.c:69-117 + bcs.c:341-347      */
 int macroc_solve_Ax(macroc_ctx *ctx, int *its, double *rnorm);   /* assembly.c:179-192 (KSPCG+PCJACOBI) */
 int macroc_ksp_reason(const macroc_ctx *ctx, int *reason);
+/* switch solve_Ax between the assembled and the matrix-free operator (cfg.op) at run time;
+ * call assembly_jac again before the next solve */
+int macroc_set_operator(macroc_ctx *ctx, int op);
 int macroc_update_u(macroc_ctx *ctx);                      /* VecAXPY(u,1,du) main.c:79 */
 int macroc_calc_B(int gp, double *B /* [6][24] */);        /* assembly.c:195-254 (host, constants) */
 int macroc_calc_force(macroc_ctx *ctx, double *force);     /* forces.c:25-166 */

@@ -35,7 +35,7 @@ EXPORTS = [
     "macroc_get_vec", "macroc_get_matrix_blocks", "macroc_matmult", "macroc_get_strain_stress",
     "macroc_time_kernel", "macroc_launch_count", "macroc_device_synchronize", "macroc_version",
     "macroc_event_record", "macroc_event_elapsed_ms", "macroc_profile_enable", "macroc_profile_get",
-    "macroc_homogenize", "macroc_gp_arrays", "macroc_set_gp_data",
+    "macroc_homogenize", "macroc_gp_arrays", "macroc_set_gp_data", "macroc_set_operator",
 ]
 
 
@@ -113,6 +113,7 @@ def lib():
     L.macroc_assembly_jac.argtypes = [vp]
     L.macroc_solve_Ax.argtypes = [vp, ip, dp]
     L.macroc_ksp_reason.argtypes = [vp, ip]
+    L.macroc_set_operator.argtypes = [vp, C.c_int]
     L.macroc_update_u.argtypes = [vp]
     L.macroc_calc_B.argtypes = [C.c_int, dp]
     L.macroc_calc_force.argtypes = [vp, dp]
@@ -310,6 +311,9 @@ class MacroC:
         its, rn = C.c_int(), C.c_double()
         self._chk(self._L.macroc_solve_Ax(self._h, C.byref(its), C.byref(rn)))
         return its.value, rn.value
+
+    def set_operator(self, op: int):
+        self._chk(self._L.macroc_set_operator(self._h, op))
 
     def ksp_reason(self) -> int:
         r = C.c_int()

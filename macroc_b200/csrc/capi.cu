@@ -42,7 +42,9 @@ struct macroc_ctx {
     double2 *A = nullptr;
     bool A_valid = false, mf_ready = false;
     double *Ke = nullptr, *T = nullptr;
-    uint8_t *nodemask = nullptr;
+    uint8_t *nodemask = nullptr, *nbflag = nullptr;
+    double *consts = nullptr;        // device copy of {dsh[192], D[36], T[6561]} for bind_constants
+    uint64_t id = 0;
     int64_t *bc_idx = nullptr;
     double *bc_coef = nullptr;
     int nbc = 0;
@@ -105,6 +107,20 @@ struct macroc_ctx {
     } while (0)
 
 static inline int cdiv64(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// __constant__ symbols are per device and shared by every context of the process on that
+// device; a context re-binds its element constants whenever another context used them last.
+static uint64_t g_next_ctx_id = 1;
+static uint64_t g_const_owner[64] = {0};
+static int bind_constants(macroc_ctx *c)
+{
+    if (c->device >= 0 && c->device < 64 && g_const_owner[c->device] == c->id) return MACROC_OK;
+    CU(c, cudaMemcpyToSymbolAsync(c_dsh, c->consts, sizeof(double) * 192, 0, cudaMemcpyDeviceToDevice, c->stream));
+    CU(c, cudaMemcpyToSymbolAsync(c_D, c->consts + 192, sizeof(double) * 36, 0, cudaMemcpyDeviceToDevice, c->stream));
+    CU(c, cudaMemcpyToSymbolAsync(c_T, c->consts + 228, sizeof(double) * 27 * 243, 0, cudaMemcpyDeviceToDevice, c->stream));
+    if (c->device >= 0 && c->device < 64) g_const_owner[c->device] = c->id;
+    return MACROC_OK;
+}
 
 extern "C" int macroc_version(void) { return 100; }
 
@@ -240,7 +256,8 @@ static int ctx_free(macroc_ctx *c)
     for (int i = 0; i < V_COUNT; ++i) cudaFree(c->vec[i]);
     cudaFree(c->A); cudaFree(c->Ke); cudaFree(c->T); cudaFree(c->nodemask); cudaFree(c->bc_idx); cudaFree(c->bc_coef);
     cudaFree(c->partial); cudaFree(c->sums); cudaFree(c->sc); cudaFree(c->stage); cudaFree(c->strain); cudaFree(c->stress);
-    cudaFree(c->ctan); cudaFree(c->scratch);
+    cudaFree(c->ctan); cudaFree(c->scratch); cudaFree(c->nbflag); cudaFree(c->consts);
+    if (c->device >= 0 && c->device < 64 && g_const_owner[c->device] == c->id) g_const_owner[c->device] = 0;
     cudaFree(c->flush);
     if (c->sums_host) cudaFreeHost(c->sums_host);
     if (c->sc_host) cudaFreeHost(c->sc_host);
@@ -272,6 +289,7 @@ extern "C" int macroc_create(const macroc_config *cfg, int rank, int nranks, con
         FAIL((macroc_ctx *)nullptr, MACROC_ERR_NO_DEVICE, "macroc_create: no CUDA device (this library has no CPU path)");
     }
     macroc_ctx *c = new macroc_ctx();
+    c->id = g_next_ctx_id++;
     c->cfg = *cfg; c->slab = slab; c->geo = make_geometry(*cfg);
     if (const char *v = getenv("MACROC_SPMV_VARIANT")) c->spmv_variant = atoi(v);
     if (cfg->device >= 0) c->device = cfg->device;
@@ -348,19 +366,24 @@ extern "C" int macroc_create(const macroc_config *cfg, int rank, int nranks, con
         }
         CUC(cudaStreamSynchronize(c->stream));
     }
-    // element constants: dsh table, D, Ke, class stencils
+    // element constants: dsh table, D, Ke, class stencils (kept in c->consts, bound on demand)
     {
         double D[36];
         if (cfg->use_D) memcpy(D, cfg->D, sizeof(D)); else isotropic_D(cfg->E, cfg->nu, D);
+        CUC(cudaMalloc(&c->consts, sizeof(double) * (228 + 27 * 243)));
+        CUC(cudaMemcpyAsync(c->consts + 192, D, sizeof(D), cudaMemcpyHostToDevice, c->stream));
         CUC(cudaMemcpyToSymbolAsync(c_D, D, sizeof(D), 0, cudaMemcpyHostToDevice, c->stream));
-        double *dsh_tmp = nullptr;
-        CUC(cudaMalloc(&dsh_tmp, sizeof(double) * 192));
-        LAUNCH(c, k_make_dsh, 1, 64, dsh_tmp);
-        CUC(cudaMemcpyToSymbolAsync(c_dsh, dsh_tmp, sizeof(double) * 192, 0, cudaMemcpyDeviceToDevice, c->stream));
+        LAUNCH(c, k_make_dsh, 1, 64, c->consts);
+        CUC(cudaMemcpyToSymbolAsync(c_dsh, c->consts, sizeof(double) * 192, 0, cudaMemcpyDeviceToDevice, c->stream));
         LAUNCH(c, k_element_matrix, 3, 192, c->geo.wg, c->Ke);
         LAUNCH(c, k_stencil_table, cdiv64(27 * 243, 256), 256, c->Ke, c->T);
+        CUC(cudaMemcpyAsync(c->consts + 228, c->T, sizeof(double) * 27 * 243, cudaMemcpyDeviceToDevice, c->stream));
+        CUC(cudaMemcpyToSymbolAsync(c_T, c->T, sizeof(double) * 27 * 243, 0, cudaMemcpyDeviceToDevice, c->stream));
+        if (c->device >= 0 && c->device < 64) g_const_owner[c->device] = c->id;
+        CUC(cudaMalloc(&c->nbflag, (size_t)g.S));
+        CUC(cudaMemsetAsync(c->nbflag, 0, (size_t)g.S, c->stream));
+        LAUNCH(c, k_nbflag, cdiv64(g.nloc, 256), 256, g, c->nodemask, c->nbflag);
         CUC(cudaStreamSynchronize(c->stream));
-        cudaFree(dsh_tmp);
         CUC(cudaGetLastError());
     }
     if (nranks > 1) {
@@ -463,6 +486,7 @@ extern "C" int macroc_set_strains(macroc_ctx *c, int materialize)
 {
     if (!c) return MACROC_ERR_ARG;
     CU(c, cudaSetDevice(c->device));
+    { int _rc = bind_constants(c); if (_rc) return _rc; }
     int rc = halo_exchange(c, c->vec[V_U], c->stream);
     if (rc) return rc;
     if (materialize || c->cfg.material == MACROC_MAT_PER_GP) {
@@ -482,6 +506,7 @@ extern "C" int macroc_homogenize(macroc_ctx *c)
     if (!c) return MACROC_ERR_ARG;
     if (c->cfg.material != MACROC_MAT_PER_GP) return MACROC_OK;
     CU(c, cudaSetDevice(c->device));
+    { int _rc = bind_constants(c); if (_rc) return _rc; }
     int rc = ensure_gp_arrays(c, true);
     if (rc) return rc;
     int64_t ngp = c->ne_owned * 8;
@@ -553,6 +578,7 @@ extern "C" int macroc_assembly_res(macroc_ctx *c, double *norm)
 {
     if (!c) return MACROC_ERR_ARG;
     CU(c, cudaSetDevice(c->device));
+    { int _rc = bind_constants(c); if (_rc) return _rc; }
     int nparts = 0;
     int rc = residual_launch(c, &nparts);
     if (rc) return rc;
@@ -581,6 +607,7 @@ extern "C" int macroc_assembly_jac(macroc_ctx *c)
 {
     if (!c) return MACROC_ERR_ARG;
     CU(c, cudaSetDevice(c->device));
+    { int _rc = bind_constants(c); if (_rc) return _rc; }
     if (c->cfg.op == MACROC_OP_MATRIX_FREE) {
         if (c->cfg.material != MACROC_MAT_UNIFORM) FAIL(c, MACROC_ERR_UNSUPPORTED, "matrix-free operator needs the uniform tangent");
         LAUNCH(c, k_mf_diag, cdiv64(c->g.nloc, 256), 256, c->g, c->T, c->nodemask, c->vec[V_DINV]);
@@ -693,8 +720,8 @@ static int apply_operator(macroc_ctx *c, int op, double *p, double *w, bool with
         int blocks;
         if (mf) {
             blocks = (int)std::min<int64_t>(cdiv64(count, 256), 148 * 8);
-            if (with_dot) LAUNCH(c, k_apply_mf<true>, blocks, 256, g, c->T, c->nodemask, p, w, first, count, c->partial + nparts, done);
-            else LAUNCH(c, k_apply_mf<false>, blocks, 256, g, c->T, c->nodemask, p, w, first, count, c->partial + nparts, done);
+            if (with_dot) LAUNCH(c, k_apply_mf<true>, blocks, 256, g, c->T, c->nodemask, c->nbflag, p, w, first, count, c->partial + nparts, done);
+            else LAUNCH(c, k_apply_mf<false>, blocks, 256, g, c->T, c->nodemask, c->nbflag, p, w, first, count, c->partial + nparts, done);
         } else {
             blocks = spmv_launch(c, p, w, first, count, c->partial + nparts, with_dot, done);
         }
@@ -765,6 +792,7 @@ extern "C" int macroc_solve_Ax(macroc_ctx *c, int *its, double *rnorm)
 {
     if (!c) return MACROC_ERR_ARG;
     CU(c, cudaSetDevice(c->device));
+    { int _rc = bind_constants(c); if (_rc) return _rc; }
     const int op = c->cfg.op;
     if (op == MACROC_OP_ASSEMBLED && !c->A_valid) FAIL(c, MACROC_ERR_ARG, "solve_Ax: assembly_jac has not been called");
     if (op == MACROC_OP_MATRIX_FREE && !c->mf_ready) FAIL(c, MACROC_ERR_ARG, "solve_Ax: assembly_jac has not been called");
@@ -809,6 +837,15 @@ extern "C" int macroc_solve_Ax(macroc_ctx *c, int *its, double *rnorm)
     return MACROC_OK;
 }
 
+extern "C" int macroc_set_operator(macroc_ctx *c, int op)
+{
+    if (!c || (op != MACROC_OP_ASSEMBLED && op != MACROC_OP_MATRIX_FREE)) return MACROC_ERR_ARG;
+    if (op == MACROC_OP_MATRIX_FREE && c->cfg.material != MACROC_MAT_UNIFORM)
+        FAIL(c, MACROC_ERR_UNSUPPORTED, "matrix-free operator needs the uniform tangent");
+    c->cfg.op = op;
+    return MACROC_OK;
+}
+
 extern "C" int macroc_ksp_reason(const macroc_ctx *c, int *reason)
 {
     if (!c || !reason) return MACROC_ERR_ARG;
@@ -830,6 +867,7 @@ extern "C" int macroc_calc_force(macroc_ctx *c, double *force)
 {
     if (!c || !force) return MACROC_ERR_ARG;
     CU(c, cudaSetDevice(c->device));
+    { int _rc = bind_constants(c); if (_rc) return _rc; }
     const Slab &s = c->slab;
     int64_t count = c->cfg.bc_type == MACROC_BC_BENDING ? (int64_t)s.ney * s.nez : (int64_t)s.nex * s.nez;
     double local = 0.;
@@ -946,6 +984,7 @@ extern "C" int macroc_matmult(macroc_ctx *c, int op, const double *x_host, doubl
 {
     if (!c || !x_host || !y_host) return MACROC_ERR_ARG;
     CU(c, cudaSetDevice(c->device));
+    { int _rc = bind_constants(c); if (_rc) return _rc; }
     if (op == MACROC_OP_ASSEMBLED && !c->A_valid) FAIL(c, MACROC_ERR_ARG, "matmult: no assembled operator");
     int64_t n = 3 * c->g.nloc;
     CU(c, cudaMemcpyAsync(c->stage, x_host, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
@@ -1029,6 +1068,7 @@ extern "C" int macroc_time_kernel(macroc_ctx *c, int what, int reps, int flush_l
 {
     if (!c || !ms_mean || reps <= 0) return MACROC_ERR_ARG;
     CU(c, cudaSetDevice(c->device));
+    { int _rc = bind_constants(c); if (_rc) return _rc; }
     const GridDev &g = c->g;
     if ((what == 0 || what == 2) && !c->A_valid) FAIL(c, MACROC_ERR_ARG, "time_kernel: assemble first");
     if (flush_l2 && !c->flush) {

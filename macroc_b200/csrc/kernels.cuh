@@ -31,6 +31,8 @@ __constant__ int c_sgn[8][3] = {{-1, -1, -1}, {+1, -1, -1}, {+1, +1, -1}, {-1, +
 // (assembly.c:198-232), filled once by k_init_dsh and then read-only.
 __constant__ double c_dsh[8][8][3];
 __constant__ double c_D[36];                 // homogenised tangent (row-major 6x6)
+// class stencils T[27 classes][27 slots][3][3] (see k_stencil_table); interior class = 13
+__constant__ double c_T[27 * 243];
 
 struct GridDev {
     int NX, NY, NZ;          // global grid
@@ -279,44 +281,86 @@ k_spmv(GridDev g, const double2 *__restrict__ A, const double *__restrict__ p, d
 // Matrix-free apply  y = (M K M + I - M) x  with the class stencils
 // (27 x 243 doubles, L1 resident): 16 B/DOF of HBM traffic, FP64-pipe bound.
 // ---------------------------------------------------------------------------
+// nbflag[node] = OR of the Dirichlet masks of the node and its 26 neighbours (0 = the
+// node's row needs no masking at all)
+__global__ void k_nbflag(GridDev g, const uint8_t *__restrict__ nodemask, uint8_t *__restrict__ nbflag)
+{
+    int64_t ln = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ln >= g.nloc) return;
+    unsigned f = 0;
+#pragma unroll
+    for (int slot = 0; slot < 27; ++slot) {
+        const int ddx = slot % 3 - 1, ddy = (slot / 3) % 3 - 1, ddz = slot / 9 - 1;
+        f |= nodemask[g.G + ln + ddx + (int64_t)g.NX * ddy + g.npl * ddz];
+    }
+    nbflag[g.G + ln] = (uint8_t)f;
+}
+
 template <bool DOT>
 __global__ void __launch_bounds__(256)
 k_apply_mf(GridDev g, const double *__restrict__ T, const uint8_t *__restrict__ nodemask,
-           const double *__restrict__ x, double *__restrict__ y, int64_t node0, int64_t nnodes,
-           double *__restrict__ partial, const int *__restrict__ done)
+           const uint8_t *__restrict__ nbflag, const double *__restrict__ x, double *__restrict__ y, int64_t node0,
+           int64_t nnodes, double *__restrict__ partial, const int *__restrict__ done)
 {
     __shared__ double sm[8];
     if (done && *done) return;
     double dot = 0.;
-    for (int64_t ln = node0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; ln < node0 + nnodes && ln < g.nloc;
-         ln += (int64_t)gridDim.x * blockDim.x) {
-        int i = (int)(ln % g.NX), j = (int)((ln / g.NX) % g.NY), k = (int)(ln / g.npl) + g.zs;
-        int type = node_class(i, g.NX) + 3 * node_class(j, g.NY) + 9 * node_class(k, g.NZ);
-        const double *Tt = T + type * 243;
-        const double *x0p = x + g.G + ln, *x1p = x0p + g.S, *x2p = x1p + g.S;
-        const uint8_t *mk = nodemask + g.G + ln;
-        const int64_t NX = g.NX, npl = g.npl;
-        double a0 = 0., a1 = 0., a2 = 0., xc0 = 0., xc1 = 0., xc2 = 0.;
-#pragma unroll
-        for (int slot = 0; slot < 27; ++slot) {
-            const int ddx = slot % 3 - 1, ddy = (slot / 3) % 3 - 1, ddz = slot / 9 - 1;
-            const int64_t off = ddx + NX * ddy + npl * ddz;
-            unsigned nb = mk[off];
-            double x0 = __ldg(x0p + off), x1 = __ldg(x1p + off), x2 = __ldg(x2p + off);
-            if (slot == 13) { xc0 = x0; xc1 = x1; xc2 = x2; }
-            x0 = (nb & 1u) ? 0. : x0; x1 = (nb & 2u) ? 0. : x1; x2 = (nb & 4u) ? 0. : x2;
-            const double *m = Tt + slot * 9;
-            a0 = fma(__ldg(m + 0), x0, a0); a0 = fma(__ldg(m + 1), x1, a0); a0 = fma(__ldg(m + 2), x2, a0);
-            a1 = fma(__ldg(m + 3), x0, a1); a1 = fma(__ldg(m + 4), x1, a1); a1 = fma(__ldg(m + 5), x2, a1);
-            a2 = fma(__ldg(m + 6), x0, a2); a2 = fma(__ldg(m + 7), x1, a2); a2 = fma(__ldg(m + 8), x2, a2);
+    const int64_t end = min(node0 + nnodes, g.nloc);
+    const int64_t NX = g.NX, npl = g.npl;
+    // warp-uniform trip count: lanes past the end stay in the loop as inactive
+    for (int64_t base = node0 + ((int64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31)); base < end;
+         base += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t ln = base + (threadIdx.x & 31);
+        const bool valid = ln < end;
+        int type = 13;
+        unsigned flag = 0;
+        if (valid) {
+            int i = (int)(ln % g.NX), j = (int)((ln / g.NX) % g.NY), k = (int)(ln / g.npl) + g.zs;
+            type = node_class(i, g.NX) + 3 * node_class(j, g.NY) + 9 * node_class(k, g.NZ);
+            flag = nbflag[g.G + ln];
         }
-        unsigned own = mk[0];
-        if (own & 1u) a0 = xc0;
-        if (own & 2u) a1 = xc1;
-        if (own & 4u) a2 = xc2;
-        double *y0 = y + g.G + ln;
-        y0[0] = a0; y0[g.S] = a1; y0[2 * g.S] = a2;
-        dot += a0 * xc0 + a1 * xc1 + a2 * xc2;
+        const int64_t lnc = valid ? ln : end - 1;           // inactive lanes read a valid address
+        const double *x0p = x + g.G + lnc, *x1p = x0p + g.S, *x2p = x1p + g.S;
+        double a0 = 0., a1 = 0., a2 = 0., xc0 = 0., xc1 = 0., xc2 = 0.;
+        if (__all_sync(0xffffffffu, type == 13 && flag == 0)) {
+            // interior warp: the stencil comes from the constant bank as an FMA operand
+#pragma unroll
+            for (int slot = 0; slot < 27; ++slot) {
+                const int ddx = slot % 3 - 1, ddy = (slot / 3) % 3 - 1, ddz = slot / 9 - 1;
+                const int64_t off = ddx + NX * ddy + npl * ddz;
+                const double x0 = __ldg(x0p + off), x1 = __ldg(x1p + off), x2 = __ldg(x2p + off);
+                if (slot == 13) { xc0 = x0; xc1 = x1; xc2 = x2; }
+                const int o = 13 * 243 + slot * 9;
+                a0 = fma(c_T[o + 0], x0, a0); a0 = fma(c_T[o + 1], x1, a0); a0 = fma(c_T[o + 2], x2, a0);
+                a1 = fma(c_T[o + 3], x0, a1); a1 = fma(c_T[o + 4], x1, a1); a1 = fma(c_T[o + 5], x2, a1);
+                a2 = fma(c_T[o + 6], x0, a2); a2 = fma(c_T[o + 7], x1, a2); a2 = fma(c_T[o + 8], x2, a2);
+            }
+        } else {
+            const double *Tt = T + type * 243;
+            const uint8_t *mk = nodemask + g.G + lnc;
+#pragma unroll 3
+            for (int slot = 0; slot < 27; ++slot) {
+                const int ddx = slot % 3 - 1, ddy = (slot / 3) % 3 - 1, ddz = slot / 9 - 1;
+                const int64_t off = ddx + NX * ddy + npl * ddz;
+                unsigned nb = mk[off];
+                double x0 = __ldg(x0p + off), x1 = __ldg(x1p + off), x2 = __ldg(x2p + off);
+                if (slot == 13) { xc0 = x0; xc1 = x1; xc2 = x2; }
+                x0 = (nb & 1u) ? 0. : x0; x1 = (nb & 2u) ? 0. : x1; x2 = (nb & 4u) ? 0. : x2;
+                const double *m = Tt + slot * 9;
+                a0 = fma(__ldg(m + 0), x0, a0); a0 = fma(__ldg(m + 1), x1, a0); a0 = fma(__ldg(m + 2), x2, a0);
+                a1 = fma(__ldg(m + 3), x0, a1); a1 = fma(__ldg(m + 4), x1, a1); a1 = fma(__ldg(m + 5), x2, a1);
+                a2 = fma(__ldg(m + 6), x0, a2); a2 = fma(__ldg(m + 7), x1, a2); a2 = fma(__ldg(m + 8), x2, a2);
+            }
+            unsigned own = mk[0];
+            if (own & 1u) a0 = xc0;
+            if (own & 2u) a1 = xc1;
+            if (own & 4u) a2 = xc2;
+        }
+        if (valid) {
+            double *y0 = y + g.G + ln;
+            y0[0] = a0; y0[g.S] = a1; y0[2 * g.S] = a2;
+            dot += a0 * xc0 + a1 * xc1 + a2 * xc2;
+        }
     }
     if (DOT) {
         double s = block_sum<8>(dot, sm);
