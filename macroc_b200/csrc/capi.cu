@@ -42,7 +42,7 @@ struct macroc_ctx {
     double2 *A = nullptr;
     bool A_valid = false, mf_ready = false;
     double *Ke = nullptr, *T = nullptr;
-    uint8_t *nodemask = nullptr, *nbflag = nullptr;
+    uint8_t *nodemask = nullptr;
     double *consts = nullptr;        // device copy of {dsh[192], D[36], T[6561]} for bind_constants
     uint64_t id = 0;
     int64_t *bc_idx = nullptr;
@@ -256,7 +256,7 @@ static int ctx_free(macroc_ctx *c)
     for (int i = 0; i < V_COUNT; ++i) cudaFree(c->vec[i]);
     cudaFree(c->A); cudaFree(c->Ke); cudaFree(c->T); cudaFree(c->nodemask); cudaFree(c->bc_idx); cudaFree(c->bc_coef);
     cudaFree(c->partial); cudaFree(c->sums); cudaFree(c->sc); cudaFree(c->stage); cudaFree(c->strain); cudaFree(c->stress);
-    cudaFree(c->ctan); cudaFree(c->scratch); cudaFree(c->nbflag); cudaFree(c->consts);
+    cudaFree(c->ctan); cudaFree(c->scratch); cudaFree(c->consts);
     if (c->device >= 0 && c->device < 64 && g_const_owner[c->device] == c->id) g_const_owner[c->device] = 0;
     cudaFree(c->flush);
     if (c->sums_host) cudaFreeHost(c->sums_host);
@@ -380,9 +380,6 @@ extern "C" int macroc_create(const macroc_config *cfg, int rank, int nranks, con
         CUC(cudaMemcpyAsync(c->consts + 228, c->T, sizeof(double) * 27 * 243, cudaMemcpyDeviceToDevice, c->stream));
         CUC(cudaMemcpyToSymbolAsync(c_T, c->T, sizeof(double) * 27 * 243, 0, cudaMemcpyDeviceToDevice, c->stream));
         if (c->device >= 0 && c->device < 64) g_const_owner[c->device] = c->id;
-        CUC(cudaMalloc(&c->nbflag, (size_t)g.S));
-        CUC(cudaMemsetAsync(c->nbflag, 0, (size_t)g.S, c->stream));
-        LAUNCH(c, k_nbflag, cdiv64(g.nloc, 256), 256, g, c->nodemask, c->nbflag);
         CUC(cudaStreamSynchronize(c->stream));
         CUC(cudaGetLastError());
     }
@@ -719,9 +716,20 @@ static int apply_operator(macroc_ctx *c, int op, double *p, double *w, bool with
         if (count <= 0) return;
         int blocks;
         if (mf) {
-            blocks = (int)std::min<int64_t>(cdiv64(count, 256), 148 * 8);
-            if (with_dot) LAUNCH(c, k_apply_mf<true>, blocks, 256, g, c->T, c->nodemask, c->nbflag, p, w, first, count, c->partial + nparts, done);
-            else LAUNCH(c, k_apply_mf<false>, blocks, 256, g, c->T, c->nodemask, c->nbflag, p, w, first, count, c->partial + nparts, done);
+            // node ranges are whole planes here
+            const int k0 = (int)(first / g.npl), k1 = (int)((first + count) / g.npl);
+            const int tiles_x = (g.NX + MF_TX - 1) / MF_TX, tiles_y = (g.NY + MF_TY - 1) / MF_TY;
+            const int64_t ntile = (int64_t)tiles_x * tiles_y * ((k1 - k0 + MF_TZ - 1) / MF_TZ);
+            static bool configured = false;
+            if (!configured) {
+                cudaFuncSetAttribute(k_apply_mf3d<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MF_SMEM);
+                cudaFuncSetAttribute(k_apply_mf3d<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MF_SMEM);
+                configured = true;
+            }
+            blocks = (int)std::min<int64_t>(ntile, 148 * 4);
+            if (with_dot) k_apply_mf3d<true><<<blocks, MF_THREADS, MF_SMEM, c->stream>>>(g, c->nodemask, p, w, k0, k1, tiles_x, tiles_y, c->partial + nparts, done);
+            else k_apply_mf3d<false><<<blocks, MF_THREADS, MF_SMEM, c->stream>>>(g, c->nodemask, p, w, k0, k1, tiles_x, tiles_y, c->partial + nparts, done);
+            c->launches++;
         } else {
             blocks = spmv_launch(c, p, w, first, count, c->partial + nparts, with_dot, done);
         }
@@ -1103,12 +1111,6 @@ extern "C" int macroc_time_kernel(macroc_ctx *c, int what, int reps, int flush_l
                 int nparts = 0;
                 rc = residual_launch(c, &nparts);
                 if (!rc) LAUNCH(c, k_reduce, 1, 256, c->partial, nparts, c->sums);
-                break;
-            }
-            case 6: {                                   // legacy node-gather residual, for comparison
-                int nblk = cdiv64(g.nloc, 128);
-                LAUNCH(c, k_residual, nblk, 128, g, c->geo.wg, c->vec[V_U], c->nodemask, c->vec[V_B], c->partial);
-                LAUNCH(c, k_reduce, 1, 256, c->partial, nblk, c->sums);
                 break;
             }
             default: FAIL(c, MACROC_ERR_ARG, "time_kernel: unknown kernel %d", what);

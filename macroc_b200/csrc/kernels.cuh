@@ -279,87 +279,141 @@ k_spmv(GridDev g, const double2 *__restrict__ A, const double *__restrict__ p, d
 
 // ---------------------------------------------------------------------------
 // Matrix-free apply  y = (M K M + I - M) x  with the class stencils
-// (27 x 243 doubles, L1 resident): 16 B/DOF of HBM traffic, FP64-pipe bound.
+// (27 x 243 doubles): 16 B/DOF of HBM traffic, FP64-pipe / issue bound.
 // ---------------------------------------------------------------------------
-// nbflag[node] = OR of the Dirichlet masks of the node and its 26 neighbours (0 = the
-// node's row needs no masking at all)
-__global__ void k_nbflag(GridDev g, const uint8_t *__restrict__ nodemask, uint8_t *__restrict__ nbflag)
-{
-    int64_t ln = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (ln >= g.nloc) return;
-    unsigned f = 0;
-#pragma unroll
-    for (int slot = 0; slot < 27; ++slot) {
-        const int ddx = slot % 3 - 1, ddy = (slot / 3) % 3 - 1, ddz = slot / 9 - 1;
-        f |= nodemask[g.G + ln + ddx + (int64_t)g.NX * ddy + g.npl * ddz];
-    }
-    nbflag[g.G + ln] = (uint8_t)f;
-}
+// 3-D tiled matrix-free apply  y = (M K M + I - M) x  on planes [k0, k1) of the slab.
+// A CTA owns MF_TX x MF_TY x MF_TZ nodes and stages the (TX+2)(TY+2)(TZ+2) x 3 patch of M x in
+// shared memory once (Dirichlet columns are zeroed while staging, so each x value is read
+// from L2 ~1.5 times instead of 27).  A thread computes a column of MF_TY nodes in y, so every
+// shared-memory operand feeds up to three output nodes (40 LDS.64 per node instead of 81);
+// for interior warps the stencil entries are immediate constant-bank operands of the DFMAs.
+constexpr int MF_TX = 32, MF_TY = 4, MF_TZ = 8;
+constexpr int MF_PX = MF_TX + 2, MF_PY = MF_TY + 2, MF_PZ = MF_TZ + 2;
+constexpr int MF_PATCH = MF_PX * MF_PY * MF_PZ;
+constexpr int MF_THREADS = MF_TX * MF_TZ;
+constexpr int MF_SMEM = (3 * MF_PATCH + 27 * 243) * (int)sizeof(double);   // patch + class table
 
 template <bool DOT>
-__global__ void __launch_bounds__(256)
-k_apply_mf(GridDev g, const double *__restrict__ T, const uint8_t *__restrict__ nodemask,
-           const uint8_t *__restrict__ nbflag, const double *__restrict__ x, double *__restrict__ y, int64_t node0,
-           int64_t nnodes, double *__restrict__ partial, const int *__restrict__ done)
+__global__ void __launch_bounds__(MF_THREADS)
+k_apply_mf3d(GridDev g, const uint8_t *__restrict__ nodemask, const double *__restrict__ x, double *__restrict__ y,
+             int k0, int k1, int tiles_x, int tiles_y, double *__restrict__ partial, const int *__restrict__ done)
 {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double(*sx)[MF_PATCH] = reinterpret_cast<double(*)[MF_PATCH]>(smem_raw);
+    double *sT = reinterpret_cast<double *>(smem_raw) + 3 * MF_PATCH;    // class stencils for boundary warps
     __shared__ double sm[8];
     if (done && *done) return;
+    for (int q = threadIdx.x; q < 27 * 243; q += MF_THREADS) sT[q] = c_T[q];
+    const int tx = threadIdx.x % MF_TX, tz = threadIdx.x / MF_TX;
+    const int64_t ntile = (int64_t)tiles_x * tiles_y * ((k1 - k0 + MF_TZ - 1) / MF_TZ);
     double dot = 0.;
-    const int64_t end = min(node0 + nnodes, g.nloc);
-    const int64_t NX = g.NX, npl = g.npl;
-    // warp-uniform trip count: lanes past the end stay in the loop as inactive
-    for (int64_t base = node0 + ((int64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31)); base < end;
-         base += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t ln = base + (threadIdx.x & 31);
-        const bool valid = ln < end;
-        int type = 13;
-        unsigned flag = 0;
-        if (valid) {
-            int i = (int)(ln % g.NX), j = (int)((ln / g.NX) % g.NY), k = (int)(ln / g.npl) + g.zs;
-            type = node_class(i, g.NX) + 3 * node_class(j, g.NY) + 9 * node_class(k, g.NZ);
-            flag = nbflag[g.G + ln];
-        }
-        const int64_t lnc = valid ? ln : end - 1;           // inactive lanes read a valid address
-        const double *x0p = x + g.G + lnc, *x1p = x0p + g.S, *x2p = x1p + g.S;
-        double a0 = 0., a1 = 0., a2 = 0., xc0 = 0., xc1 = 0., xc2 = 0.;
-        if (__all_sync(0xffffffffu, type == 13 && flag == 0)) {
-            // interior warp: the stencil comes from the constant bank as an FMA operand
+    for (int64_t t = blockIdx.x; t < ntile; t += gridDim.x) {
+        const int i0 = (int)(t % tiles_x) * MF_TX, j0 = (int)((t / tiles_x) % tiles_y) * MF_TY;
+        const int kk0 = k0 + (int)(t / ((int64_t)tiles_x * tiles_y)) * MF_TZ;       // slab-local plane
+        __syncthreads();
+        {
+            // all loads of the patch are issued before the first use (independent of the masks)
+            constexpr int NIT = (MF_PATCH + MF_THREADS - 1) / MF_THREADS;
+            double v0[NIT], v1[NIT], v2[NIT];
+            unsigned mk[NIT];
 #pragma unroll
-            for (int slot = 0; slot < 27; ++slot) {
-                const int ddx = slot % 3 - 1, ddy = (slot / 3) % 3 - 1, ddz = slot / 9 - 1;
-                const int64_t off = ddx + NX * ddy + npl * ddz;
-                const double x0 = __ldg(x0p + off), x1 = __ldg(x1p + off), x2 = __ldg(x2p + off);
-                if (slot == 13) { xc0 = x0; xc1 = x1; xc2 = x2; }
-                const int o = 13 * 243 + slot * 9;
-                a0 = fma(c_T[o + 0], x0, a0); a0 = fma(c_T[o + 1], x1, a0); a0 = fma(c_T[o + 2], x2, a0);
-                a1 = fma(c_T[o + 3], x0, a1); a1 = fma(c_T[o + 4], x1, a1); a1 = fma(c_T[o + 5], x2, a1);
-                a2 = fma(c_T[o + 6], x0, a2); a2 = fma(c_T[o + 7], x1, a2); a2 = fma(c_T[o + 8], x2, a2);
+            for (int it = 0; it < NIT; ++it) {
+                const int q = threadIdx.x + it * MF_THREADS;
+                const int px = q % MF_PX, py = (q / MF_PX) % MF_PY, pz = q / (MF_PX * MF_PY);
+                const int i = i0 + px - 1;
+                const int64_t ln = (int64_t)(kk0 + pz - 1) * g.npl + (int64_t)(j0 + py - 1) * g.NX + i;
+                const bool ok = q < MF_PATCH && i <= g.NX && ln >= -(int64_t)g.G && g.G + ln < g.S;
+                const int64_t idx = g.G + (ok ? ln : 0);
+                mk[it] = ok ? nodemask[idx] : 7u;
+                v0[it] = __ldg(x + idx); v1[it] = __ldg(x + g.S + idx); v2[it] = __ldg(x + 2 * g.S + idx);
             }
-        } else {
-            const double *Tt = T + type * 243;
-            const uint8_t *mk = nodemask + g.G + lnc;
-#pragma unroll 3
-            for (int slot = 0; slot < 27; ++slot) {
-                const int ddx = slot % 3 - 1, ddy = (slot / 3) % 3 - 1, ddz = slot / 9 - 1;
-                const int64_t off = ddx + NX * ddy + npl * ddz;
-                unsigned nb = mk[off];
-                double x0 = __ldg(x0p + off), x1 = __ldg(x1p + off), x2 = __ldg(x2p + off);
-                if (slot == 13) { xc0 = x0; xc1 = x1; xc2 = x2; }
-                x0 = (nb & 1u) ? 0. : x0; x1 = (nb & 2u) ? 0. : x1; x2 = (nb & 4u) ? 0. : x2;
-                const double *m = Tt + slot * 9;
-                a0 = fma(__ldg(m + 0), x0, a0); a0 = fma(__ldg(m + 1), x1, a0); a0 = fma(__ldg(m + 2), x2, a0);
-                a1 = fma(__ldg(m + 3), x0, a1); a1 = fma(__ldg(m + 4), x1, a1); a1 = fma(__ldg(m + 5), x2, a1);
-                a2 = fma(__ldg(m + 6), x0, a2); a2 = fma(__ldg(m + 7), x1, a2); a2 = fma(__ldg(m + 8), x2, a2);
+#pragma unroll
+            for (int it = 0; it < NIT; ++it) {
+                const int q = threadIdx.x + it * MF_THREADS;
+                if (q < MF_PATCH) {
+                    sx[0][q] = (mk[it] & 1u) ? 0. : v0[it];
+                    sx[1][q] = (mk[it] & 2u) ? 0. : v1[it];
+                    sx[2][q] = (mk[it] & 4u) ? 0. : v2[it];
+                }
             }
-            unsigned own = mk[0];
-            if (own & 1u) a0 = xc0;
-            if (own & 2u) a1 = xc1;
-            if (own & 4u) a2 = xc2;
         }
-        if (valid) {
-            double *y0 = y + g.G + ln;
-            y0[0] = a0; y0[g.S] = a1; y0[2 * g.S] = a2;
-            dot += a0 * xc0 + a1 * xc1 + a2 * xc2;
+        __syncthreads();
+        const int i = i0 + tx, kl = kk0 + tz;
+        const bool col_valid = i < g.NX && kl < k1;
+        const int cx = node_class(i, g.NX), cz = node_class(kl + g.zs, g.NZ);
+        int type[MF_TY];
+        bool interior = true;
+#pragma unroll
+        for (int jj = 0; jj < MF_TY; ++jj) {
+            const int j = j0 + jj;
+            type[jj] = (col_valid && j < g.NY) ? cx + 3 * node_class(j, g.NY) + 9 * cz : 13;
+            interior = interior && type[jj] == 13;
+        }
+        double acc[MF_TY][3];
+#pragma unroll
+        for (int jj = 0; jj < MF_TY; ++jj) acc[jj][0] = acc[jj][1] = acc[jj][2] = 0.;
+        const int cbase = ((tz + 1) * MF_PY) * MF_PX + tx + 1;          // patch row py = 0 of this column
+        if (__all_sync(0xffffffffu, interior)) {
+#pragma unroll
+            for (int dz = -1; dz <= 1; ++dz)
+#pragma unroll
+                for (int py = 0; py < MF_PY; ++py)
+#pragma unroll
+                    for (int dx = -1; dx <= 1; ++dx) {
+                        const int o = cbase + (dz * MF_PY + py) * MF_PX + dx;
+                        const double x0 = sx[0][o], x1 = sx[1][o], x2 = sx[2][o];
+#pragma unroll
+                        for (int jj = 0; jj < MF_TY; ++jj) {
+                            const int ddy = py - 1 - jj;
+                            if (ddy < -1 || ddy > 1) continue;
+                            const int ct = 13 * 243 + ((dz + 1) * 9 + (ddy + 1) * 3 + (dx + 1)) * 9;
+                            acc[jj][0] = fma(c_T[ct + 0], x0, acc[jj][0]); acc[jj][0] = fma(c_T[ct + 1], x1, acc[jj][0]); acc[jj][0] = fma(c_T[ct + 2], x2, acc[jj][0]);
+                            acc[jj][1] = fma(c_T[ct + 3], x0, acc[jj][1]); acc[jj][1] = fma(c_T[ct + 4], x1, acc[jj][1]); acc[jj][1] = fma(c_T[ct + 5], x2, acc[jj][1]);
+                            acc[jj][2] = fma(c_T[ct + 6], x0, acc[jj][2]); acc[jj][2] = fma(c_T[ct + 7], x1, acc[jj][2]); acc[jj][2] = fma(c_T[ct + 8], x2, acc[jj][2]);
+                        }
+                    }
+        } else {
+            // boundary classes: per-node class offsets into the shared-memory copy of the table
+            // (lanes of one class broadcast; divergent constant-bank reads would serialise)
+#pragma unroll 1
+            for (int dz = -1; dz <= 1; ++dz)
+#pragma unroll 1
+                for (int py = 0; py < MF_PY; ++py)
+#pragma unroll
+                    for (int dx = -1; dx <= 1; ++dx) {
+                        const int o = cbase + (dz * MF_PY + py) * MF_PX + dx;
+                        const double x0 = sx[0][o], x1 = sx[1][o], x2 = sx[2][o];
+#pragma unroll
+                        for (int jj = 0; jj < MF_TY; ++jj) {
+                            const int ddy = py - 1 - jj;
+                            if (ddy < -1 || ddy > 1) continue;
+                            const double *m = sT + type[jj] * 243 + ((dz + 1) * 9 + (ddy + 1) * 3 + (dx + 1)) * 9;
+                            acc[jj][0] = fma(m[0], x0, acc[jj][0]); acc[jj][0] = fma(m[1], x1, acc[jj][0]); acc[jj][0] = fma(m[2], x2, acc[jj][0]);
+                            acc[jj][1] = fma(m[3], x0, acc[jj][1]); acc[jj][1] = fma(m[4], x1, acc[jj][1]); acc[jj][1] = fma(m[5], x2, acc[jj][1]);
+                            acc[jj][2] = fma(m[6], x0, acc[jj][2]); acc[jj][2] = fma(m[7], x1, acc[jj][2]); acc[jj][2] = fma(m[8], x2, acc[jj][2]);
+                        }
+                    }
+        }
+        if (col_valid) {
+#pragma unroll
+            for (int jj = 0; jj < MF_TY; ++jj) {
+                const int j = j0 + jj;
+                if (j >= g.NY) continue;
+                const int64_t ln = (int64_t)kl * g.npl + (int64_t)j * g.NX + i;
+                const unsigned own = nodemask[g.G + ln];
+                const int c0 = cbase + (jj + 1) * MF_PX;
+                double xc0 = sx[0][c0], xc1 = sx[1][c0], xc2 = sx[2][c0];
+                double a0 = acc[jj][0], a1 = acc[jj][1], a2 = acc[jj][2];
+                if (own) {                       // Dirichlet rows are identity rows: y = x (unmasked)
+                    const double *xo = x + g.G + ln;
+                    if (own & 1u) { xc0 = __ldg(xo); a0 = xc0; }
+                    if (own & 2u) { xc1 = __ldg(xo + g.S); a1 = xc1; }
+                    if (own & 4u) { xc2 = __ldg(xo + 2 * g.S); a2 = xc2; }
+                }
+                double *y0 = y + g.G + ln;
+                y0[0] = a0; y0[g.S] = a1; y0[2 * g.S] = a2;
+                dot += a0 * xc0 + a1 * xc1 + a2 * xc2;
+            }
         }
     }
     if (DOT) {
@@ -387,10 +441,10 @@ __global__ void k_mf_diag(GridDev g, const double *__restrict__ T, const uint8_t
 // ---------------------------------------------------------------------------
 // Residual  b = -(sum_e sum_gp B^T sigma wg), Dirichlet rows -> 0, + |b|^2
 // (set_strains assembly.c:25-66, sigma = D eps, assembly_res :120-176).
-// Gather form: one thread per owned node walks its <= 8 elements in increasing
-// element order (the reference's accumulation order), so no atomics, no
-// colouring and no reverse halo: the element layer above the slab is
-// integrated redundantly from the upper ghost plane of u.
+// The kernels are in assembly_elem.cuh (element forces -> per-node gather in
+// increasing element order: no atomics, no colouring, no reverse halo -- the
+// element layer above the slab is integrated redundantly from the upper ghost
+// plane of u).  The element-level helpers below are shared with them.
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ void element_strain(const double (&ue)[8][3], int gp, double (&eps)[6])
 {
@@ -430,50 +484,6 @@ __device__ __forceinline__ void gather_element(const double *__restrict__ u, con
 #pragma unroll
         for (int d = 0; d < 3; ++d) ue[n][d] = __ldg(u + d * g.S + q);
     }
-}
-
-__global__ void __launch_bounds__(128)
-k_residual(GridDev g, double wg, const double *__restrict__ u, const uint8_t *__restrict__ nodemask,
-           double *__restrict__ b, double *__restrict__ partial)
-{
-    __shared__ double sm[4];
-    int64_t ln = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    double sq = 0.;
-    if (ln < g.nloc) {
-        int i = (int)(ln % g.NX), j = (int)((ln / g.NX) % g.NY), k = (int)(ln / g.npl) + g.zs;
-        double r0 = 0., r1 = 0., r2 = 0.;
-        for (int oz = -1; oz <= 0; ++oz)
-            for (int oy = -1; oy <= 0; ++oy)
-                for (int ox = -1; ox <= 0; ++ox) {
-                    int ei = i + ox, ej = j + oy, ek = k + oz;
-                    if (ei < 0 || ei >= g.NX - 1 || ej < 0 || ej >= g.NY - 1 || ek < 0 || ek >= g.NZ - 1) continue;
-                    int a = local_node_of_pos(-ox, -oy, -oz);
-                    double ue[8][3];
-                    gather_element(u, g, g.G + ln + ox + (int64_t)g.NX * oy + g.npl * oz, ue);
-                    double be0 = 0., be1 = 0., be2 = 0.;
-#pragma unroll
-                    for (int gp = 0; gp < 8; ++gp) {
-                        double eps[6], sig[6];
-                        element_strain(ue, gp, eps);
-                        stress_of(eps, sig);
-                        const double hx = c_dsh[gp][a][0], hy = c_dsh[gp][a][1], hz = c_dsh[gp][a][2];
-                        // be[i] += B[j][i]*stress[j]*wg, j ascending (assembly.c:151-153)
-                        be0 += hx * sig[0] * wg; be0 += hy * sig[3] * wg; be0 += hz * sig[4] * wg;
-                        be1 += hy * sig[1] * wg; be1 += hx * sig[3] * wg; be1 += hz * sig[5] * wg;
-                        be2 += hz * sig[2] * wg; be2 += hx * sig[4] * wg; be2 += hy * sig[5] * wg;
-                    }
-                    r0 += be0; r1 += be1; r2 += be2;
-                }
-        unsigned own = nodemask[g.G + ln];
-        r0 = (own & 1u) ? 0. : -r0;      // apply_bc_on_res (bcs.c:350-362) + VecScale(-1) (:173)
-        r1 = (own & 2u) ? 0. : -r1;
-        r2 = (own & 4u) ? 0. : -r2;
-        double *b0 = b + g.G + ln;
-        b0[0] = r0; b0[g.S] = r1; b0[2 * g.S] = r2;
-        sq = r0 * r0 + r1 * r1 + r2 * r2;
-    }
-    double s = block_sum<4>(sq, sm);
-    if (threadIdx.x == 0) partial[blockIdx.x] = s;
 }
 
 // set_strains with materialisation: strain/stress[gpi*6 + i], gpi = ie*8 + gp
