@@ -882,7 +882,8 @@ extern "C" int macroc_calc_force(macroc_ctx *c, double *force)
     if (count > 0) {
         int nblk = cdiv64(count, 128);
         LAUNCH(c, k_force, nblk, 128, c->g, s.ezs, s.nez, c->cfg.bc_type, c->geo.dx, c->geo.dy, c->geo.dz, c->cfg.lx,
-               c->cfg.lz, c->geo.rad, c->vec[V_U], c->partial);
+               c->cfg.lz, c->geo.rad, c->vec[V_U],
+               (c->cfg.material == MACROC_MAT_PER_GP && c->stress) ? c->stress : (const double *)nullptr, c->partial);
         LAUNCH(c, k_reduce, 1, 256, c->partial, nblk, c->sums);
     } else
         CU(c, cudaMemsetAsync(c->sums, 0, sizeof(double), c->stream));

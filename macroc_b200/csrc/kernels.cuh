@@ -516,7 +516,7 @@ k_strain_stress(GridDev g, int ezs, int nez, const double *__restrict__ u, doubl
 // next to the loaded boundary, component [3]*dy*dz (bending) or [1]*dx*dz (circle).
 __global__ void __launch_bounds__(128)
 k_force(GridDev g, int ezs, int nez, int bc_type, double dx, double dy, double dz, double lx, double lz,
-        double rad, const double *__restrict__ u, double *__restrict__ partial)
+        double rad, const double *__restrict__ u, const double *__restrict__ stress_gp, double *__restrict__ partial)
 {
     __shared__ double sm[4];
     int64_t nex = g.NX - 1, ney = g.NY - 1;
@@ -536,17 +536,22 @@ k_force(GridDev g, int ezs, int nez, int bc_type, double dx, double dy, double d
             take = (__dadd_rn(__dmul_rn(xx, xx), __dmul_rn(zz, zz))) < rad * rad;
         }
         if (take) {
-            int64_t base = g.G + ei + (int64_t)g.NX * ej + g.npl * (ek - g.zs);
-            double ue[8][3];
-            gather_element(u, g, base, ue);
             double ave = 0.;
             const int comp = bc_type == 0 ? 3 : 1;
+            if (stress_gp) {                      // Gauss-point stresses of the material plug-in (forces.c:85,149)
+                const int64_t e = ei + nex * (ej + ney * (int64_t)(ek - ezs));
+                for (int gp = 0; gp < 8; ++gp) ave += stress_gp[(e * 8 + gp) * 6 + comp];
+            } else {
+                int64_t base = g.G + ei + (int64_t)g.NX * ej + g.npl * (ek - g.zs);
+                double ue[8][3];
+                gather_element(u, g, base, ue);
 #pragma unroll
-            for (int gp = 0; gp < 8; ++gp) {
-                double eps[6], sig[6];
-                element_strain(ue, gp, eps);
-                stress_of(eps, sig);
-                ave += sig[comp];
+                for (int gp = 0; gp < 8; ++gp) {
+                    double eps[6], sig[6];
+                    element_strain(ue, gp, eps);
+                    stress_of(eps, sig);
+                    ave += sig[comp];
+                }
             }
             f = bc_type == 0 ? ave * dy * dz : ave * dx * dz;
         }

@@ -32,16 +32,10 @@ GRIDS = [
 ]
 
 
-def pair(NX, NY, NZ, bc, extra, **kw):
-    o = O.Oracle(O.Config(NX=NX, NY=NY, NZ=NZ, bc_type=bc, faithful_ke=0, **extra, **kw))
-    m = M.MacroC(M.Config(NX=NX, NY=NY, NZ=NZ, bc_type=bc, **extra,
-                          **{k.replace("rtol", "ksp_rtol") if k == "rtol" else k: v for k, v in kw.items()}))
-    return o, m
-
-
 @pytest.mark.parametrize("NX,NY,NZ,bc,extra", GRIDS)
 def test_one_newton_step_function_by_function(NX, NY, NZ, bc, extra):
-    o, m = pair(NX, NY, NZ, bc, extra)
+    o = O.Oracle(O.Config(NX=NX, NY=NY, NZ=NZ, bc_type=bc, faithful_ke=0, **extra))
+    m = M.MacroC(M.Config(NX=NX, NY=NY, NZ=NZ, bc_type=bc, **extra))
     rng = np.random.default_rng(7)
     # start from a non-trivial state so the residual exercises every element
     u0 = 1e-3 * rng.standard_normal(o.ndof)
@@ -288,3 +282,32 @@ def test_heterogeneous_gauss_point_data():
     assert rel_err(m.get_matrix_blocks(), A_ref) < TOL_MAT
     x = rng.standard_normal(n)
     assert rel_err(m.matmult(x), A @ x) < 1e-13
+
+
+def test_two_live_contexts_do_not_share_element_constants():
+    """__constant__ tables are per device: contexts with different material / element size must
+    re-bind them when they interleave."""
+    a_kw = dict(NX=9, NY=5, NZ=6, bc_type=M.BC_BENDING, lx=10., ly=1., lz=1.)
+    b_kw = dict(NX=9, NY=5, NZ=6, bc_type=M.BC_BENDING, lx=3., ly=2., lz=5., E=2.0e6, nu=0.3)
+    ma, mb = M.MacroC(M.Config(**a_kw)), M.MacroC(M.Config(**b_kw))
+    oa, ob = O.Oracle(O.Config(faithful_ke=0, **a_kw)), O.Oracle(O.Config(faithful_ke=0, **b_kw))
+    x = np.random.default_rng(9).standard_normal(oa.ndof)
+    for m, o in ((ma, oa), (mb, ob), (ma, oa), (mb, ob)):
+        o.set_vec("u", 1e-3 * x); m.set_vec(M.VEC_U, 1e-3 * x)
+        o.set_strains(); o.homogenize(); m.set_strains()
+        assert m.assembly_res() == pytest.approx(o.assembly_res(), rel=1e-12)
+        o.assembly_jac(); m.assembly_jac()
+        assert np.array_equal(m.get_matrix_blocks(), o.block_stencil())
+        assert rel_err(m.matmult(x, M.OP_MATRIX_FREE), o.matmult(x)) < 1e-13
+
+
+def test_force_from_plugin_stresses():
+    """calc_force reads the Gauss-point stress array in MACROC_MAT_PER_GP mode (forces.c:85)."""
+    kw = dict(NX=6, NY=4, NZ=5, bc_type=M.BC_BENDING)
+    m = M.MacroC(M.Config(material=M.MAT_PER_GP, **kw))
+    ne = 5 * 3 * 4
+    stress = np.random.default_rng(2).standard_normal((ne, 8, 6))
+    m.set_strains(); m.set_gp_data(stress=stress)
+    dy, dz = 1.0 / 3, 50.0 / 4
+    expect = sum(stress[(6 - 2) + ey * 5 + ez * 15, :, 3].sum() * dy * dz for ey in range(3) for ez in range(4))
+    assert m.calc_force() == pytest.approx(expect, rel=1e-12)
