@@ -637,6 +637,10 @@ __global__ void k_fill_pattern(GridDev g, const uint8_t *__restrict__ nodemask, 
 // PCG (KSPCG + PCJACOBI, PETSc semantics -- SURVEY.md 8c item 6)
 // ---------------------------------------------------------------------------
 
+// The vector kernels below walk the owned range two nodes at a time with 128-bit accesses
+// (S and G are multiples of 32, so component bases are 16-byte aligned); npair = ceil(nloc/2),
+// the odd tail element is handled by predication inside the pair.
+
 // r = b, x = 0, z = r*dinv; partials of z.z and z.r
 __global__ void __launch_bounds__(256)
 k_cg_init(GridDev g, const double *__restrict__ b, const double *__restrict__ dinv, double *__restrict__ x,
@@ -644,13 +648,22 @@ k_cg_init(GridDev g, const double *__restrict__ b, const double *__restrict__ di
 {
     __shared__ double sm[8];
     double zz = 0., zr = 0.;
-    for (int64_t ln = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; ln < g.nloc; ln += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t npair = (g.nloc + 1) >> 1;
+    for (int64_t pr = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; pr < npair; pr += (int64_t)gridDim.x * blockDim.x) {
+        const bool two = 2 * pr + 1 < g.nloc;
 #pragma unroll
         for (int d = 0; d < 3; ++d) {
-            int64_t q = d * g.S + g.G + ln;
-            double rv = b[q], z = rv * dinv[q];
-            x[q] = 0.; r[q] = rv;
-            zz = fma(z, z, zz); zr = fma(z, rv, zr);
+            const int64_t q = d * g.S + g.G + 2 * pr;
+            const double2 bv = *reinterpret_cast<const double2 *>(b + q), dv = *reinterpret_cast<const double2 *>(dinv + q);
+            double2 rv = bv;
+            if (!two) rv.y = 0.;
+            const double z0 = rv.x * dv.x, z1 = two ? rv.y * dv.y : 0.;
+            if (two) {
+                *reinterpret_cast<double2 *>(x + q) = make_double2(0., 0.);
+                *reinterpret_cast<double2 *>(r + q) = rv;
+            } else { x[q] = 0.; r[q] = rv.x; }
+            zz = fma(z0, z0, zz); zr = fma(z0, rv.x, zr);
+            zz = fma(z1, z1, zz); zr = fma(z1, rv.y, zr);
         }
     }
     double s0 = block_sum<8>(zz, sm), s1 = block_sum<8>(zr, sm);
@@ -678,12 +691,19 @@ k_cg_update_p(GridDev g, const CgScalars *__restrict__ s, const double *__restri
     if (s->done) return;
     const bool first = s->its == 0;
     const double bb = s->beta / s->betaold;
-    for (int64_t ln = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; ln < g.nloc; ln += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t npair = (g.nloc + 1) >> 1;
+    for (int64_t pr = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; pr < npair; pr += (int64_t)gridDim.x * blockDim.x) {
+        const bool two = 2 * pr + 1 < g.nloc;
 #pragma unroll
         for (int d = 0; d < 3; ++d) {
-            int64_t q = d * g.S + g.G + ln;
-            double z = r[q] * dinv[q];
-            p[q] = first ? z : fma(bb, p[q], z);
+            const int64_t q = d * g.S + g.G + 2 * pr;
+            const double2 rv = *reinterpret_cast<const double2 *>(r + q), dv = *reinterpret_cast<const double2 *>(dinv + q);
+            double2 pv = *reinterpret_cast<const double2 *>(p + q);
+            const double z0 = rv.x * dv.x, z1 = rv.y * dv.y;
+            pv.x = first ? z0 : fma(bb, pv.x, z0);
+            pv.y = first ? z1 : fma(bb, pv.y, z1);
+            if (two) *reinterpret_cast<double2 *>(p + q) = pv;
+            else p[q] = pv.x;
         }
     }
 }
@@ -697,18 +717,27 @@ k_cg_update_xr(GridDev g, const CgScalars *__restrict__ s, const double *__restr
     __shared__ double sm[8];
     if (s->done) return;
     const double pw = s->pw;
-    if (pw == 0.) return;                      // KSP_DIVERGED_INDEFINITE_MAT, flagged by k_cg_scalars_iter
+    if (pw == 0.) return;                      // KSP_DIVERGED_INDEFINITE_MAT, flagged by the scalar update
     const double a = s->beta / pw;
     double zz = 0., zr = 0.;
-    for (int64_t ln = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; ln < g.nloc; ln += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t npair = (g.nloc + 1) >> 1;
+    for (int64_t pr = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; pr < npair; pr += (int64_t)gridDim.x * blockDim.x) {
+        const bool two = 2 * pr + 1 < g.nloc;
 #pragma unroll
         for (int d = 0; d < 3; ++d) {
-            int64_t q = d * g.S + g.G + ln;
-            x[q] = fma(a, p[q], x[q]);
-            double rv = fma(-a, w[q], r[q]);
-            r[q] = rv;
-            double z = rv * dinv[q];
-            zz = fma(z, z, zz); zr = fma(z, rv, zr);
+            const int64_t q = d * g.S + g.G + 2 * pr;
+            const double2 pv = *reinterpret_cast<const double2 *>(p + q), wv = *reinterpret_cast<const double2 *>(w + q);
+            const double2 dv = *reinterpret_cast<const double2 *>(dinv + q);
+            double2 xv = *reinterpret_cast<const double2 *>(x + q), rv = *reinterpret_cast<const double2 *>(r + q);
+            xv.x = fma(a, pv.x, xv.x); xv.y = fma(a, pv.y, xv.y);
+            rv.x = fma(-a, wv.x, rv.x); rv.y = fma(-a, wv.y, rv.y);
+            if (two) {
+                *reinterpret_cast<double2 *>(x + q) = xv;
+                *reinterpret_cast<double2 *>(r + q) = rv;
+            } else { x[q] = xv.x; r[q] = rv.x; rv.y = 0.; }
+            const double z0 = rv.x * dv.x, z1 = two ? rv.y * dv.y : 0.;
+            zz = fma(z0, z0, zz); zr = fma(z0, rv.x, zr);
+            zz = fma(z1, z1, zz); zr = fma(z1, rv.y, zr);
         }
     }
     double s0 = block_sum<8>(zz, sm), s1 = block_sum<8>(zr, sm);
