@@ -158,8 +158,9 @@ int macroc_get_strain_stress(macroc_ctx *ctx, double *strain, double *stress, in
  * already resident in HBM and returns the mean device time per launch in ms
  * (CUDA events on that stream).  what: 0 SpMV assembled, 1 apply matrix-free,
  * 2 one full PCG iteration (assembled), 3 Jacobian assembly, 4 residual,
- * 5 one full PCG iteration (matrix-free).  flush_l2 != 0 writes a >L2 buffer
- * between launches. */
+ * 5 one full PCG iteration (matrix-free), 7 per-element Jacobian kernel.
+ * flush_l2 != 0 writes a >L2 buffer between launches.  Clobbers b, du and the
+ * KSP work vectors (2, 5) -- a measurement hook, not part of the solve path. */
 int macroc_time_kernel(macroc_ctx *ctx, int what, int reps, int flush_l2, double *ms_mean);
 uint64_t macroc_launch_count(const macroc_ctx *ctx);       /* kernels launched so far */
 /* CUDA-event stopwatch on the context's stream (slots 0..7): record, then

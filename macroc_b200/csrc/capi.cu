@@ -729,7 +729,9 @@ static int apply_operator(macroc_ctx *c, int op, double *p, double *w, bool with
                 cudaFuncSetAttribute(k_apply_mf3d<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MF_SMEM);
                 configured = true;
             }
-            blocks = (int)std::min<int64_t>(ntile, 148 * 4);
+            // an odd grid: the tile -> CTA map must not be periodic in the 8 x-tiles of a row, or the
+            // CTAs that always get a boundary column finish last
+            blocks = (int)std::min<int64_t>(ntile, 148 * 4 - 1);
             if (with_dot) k_apply_mf3d<true><<<blocks, MF_THREADS, MF_SMEM, c->stream>>>(g, c->nodemask, p, w, k0, k1, tiles_x, tiles_y, c->partial + nparts, done);
             else k_apply_mf3d<false><<<blocks, MF_THREADS, MF_SMEM, c->stream>>>(g, c->nodemask, p, w, k0, k1, tiles_x, tiles_y, c->partial + nparts, done);
             c->launches++;
@@ -1138,6 +1140,13 @@ extern "C" int macroc_time_kernel(macroc_ctx *c, int what, int reps, int flush_l
                 int nparts = 0;
                 rc = residual_launch(c, &nparts);
                 if (!rc) LAUNCH(c, k_reduce, 1, 256, c->partial, nparts, c->sums);
+                break;
+            }
+            case 7: {                                   // per-element Jacobian kernel (tangent source per cfg.material)
+                int save_op = c->cfg.op, save_j = c->cfg.jac_mode;
+                c->cfg.op = MACROC_OP_ASSEMBLED; c->cfg.jac_mode = MACROC_JAC_ELEMENT;
+                rc = macroc_assembly_jac(c);
+                c->cfg.op = save_op; c->cfg.jac_mode = save_j;
                 break;
             }
             default: FAIL(c, MACROC_ERR_ARG, "time_kernel: unknown kernel %d", what);

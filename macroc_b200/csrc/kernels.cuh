@@ -288,7 +288,10 @@ k_spmv(GridDev g, const double2 *__restrict__ A, const double *__restrict__ p, d
 // shared-memory operand feeds up to three output nodes (40 LDS.64 per node instead of 81);
 // for interior warps the stencil entries are immediate constant-bank operands of the DFMAs.
 constexpr int MF_TX = 32, MF_TY = 4, MF_TZ = 8;
-constexpr int MF_PX = MF_TX + 2, MF_PY = MF_TY + 2, MF_PZ = MF_TZ + 2;
+// patch pitch: PX = TX + 2 rounded so that PY*PX = 8 (mod 16) doubles -- a warp is 8 (x) x 4 (z)
+// lanes and its four z-rows then fall into disjoint shared-memory bank halves (no conflicts)
+constexpr int MF_PX = MF_TX + 4, MF_PY = MF_TY + 2, MF_PZ = MF_TZ + 2;
+static_assert((MF_PX * MF_PY) % 16 == 8, "bank-conflict-free z pitch");
 constexpr int MF_PATCH = MF_PX * MF_PY * MF_PZ;
 constexpr int MF_THREADS = MF_TX * MF_TZ;
 constexpr int MF_SMEM = (3 * MF_PATCH + 27 * 243) * (int)sizeof(double);   // patch + class table
@@ -304,7 +307,10 @@ k_apply_mf3d(GridDev g, const uint8_t *__restrict__ nodemask, const double *__re
     __shared__ double sm[8];
     if (done && *done) return;
     for (int q = threadIdx.x; q < 27 * 243; q += MF_THREADS) sT[q] = c_T[q];
-    const int tx = threadIdx.x % MF_TX, tz = threadIdx.x / MF_TX;
+    // warp w = x-block (w % 4) of 8 nodes, z-block (w / 4) of 4 planes; lane = 8 (x) x 4 (z): only
+    // 2 of the 32 x-blocks of a row touch the x faces (a 32-wide warp would put 2 of 8 there)
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tx = (warp & 3) * 8 + (lane & 7), tz = (warp >> 2) * 4 + (lane >> 3);
     const int64_t ntile = (int64_t)tiles_x * tiles_y * ((k1 - k0 + MF_TZ - 1) / MF_TZ);
     double dot = 0.;
     for (int64_t t = blockIdx.x; t < ntile; t += gridDim.x) {
