@@ -118,10 +118,17 @@ int macroc_set_strains(macroc_ctx *ctx, int materialize);
  * for every owned Gauss point, on the device.  A GPU material model replaces this call by
  * writing the arrays of macroc_gp_arrays itself.  No-op for MACROC_MAT_UNIFORM. */
 int macroc_homogenize(macroc_ctx *ctx);
-/* DEVICE pointers to the Gauss-point arrays (gpi = ie*8+gp over the rank's DMDA-owned
- * elements, assembly.c:58,91,148): strain/stress 6 doubles, ctan 36 doubles per point. */
-int macroc_gp_arrays(macroc_ctx *ctx, double **strain, double **stress, double **ctan, int64_t *n_gp);
-/* host -> device copies into those arrays (tests, CPU material models); NULL = leave as is */
+/* DEVICE pointers to the Gauss-point arrays of the rank's DMDA-owned elements (the data the
+ * reference exchanges with MicroPP at gpi = ie*8+gp, assembly.c:58,91,148).  On the device they
+ * are SoA over elements so that consecutive lanes touch consecutive doubles:
+ *     strain/stress[(gp*6 + i) * pitch + ie],   ctan[((gp*6 + k)*6 + l) * pitch + ie],
+ * ie = rank-local element in DMDAGetElements order, pitch returned in *pitch (>= n_gp/8; the
+ * tail holds the upper neighbour's first element layer).  A GPU material model reads strain
+ * and writes stress and ctan in place. */
+int macroc_gp_arrays(macroc_ctx *ctx, double **strain, double **stress, double **ctan, int64_t *n_gp,
+                     int64_t *pitch);
+/* host -> device copies into those arrays in the reference's AoS view, stress[gpi*6 + i],
+ * ctan[gpi*36 + 6k + l] (tests, CPU material models); NULL = leave as is */
 int macroc_set_gp_data(macroc_ctx *ctx, const double *stress_host, const double *ctan_host);
 int macroc_assembly_res(macroc_ctx *ctx, double *norm);    /* assembly.c:120-176 + VecNorm main.c:67 */
 int macroc_assembly_jac(macroc_ctx *ctx);                  /* assembly.c:69-117 + bcs.c:341-347      */
@@ -151,6 +158,7 @@ int macroc_get_matrix_blocks(macroc_ctx *ctx, double *host);
 /* y = A x with the assembled (op = 0) or matrix-free (op = 1) operator; x, y on
  * the host in boundary layout (halo exchanged internally). */
 int macroc_matmult(macroc_ctx *ctx, int op, const double *x_host, double *y_host);
+/* Gauss-point strain / stress in the reference's AoS view ([gpi*6 + i], gpi = ie*8+gp) */
 int macroc_get_strain_stress(macroc_ctx *ctx, double *strain, double *stress, int64_t *n_gp);
 
 /* ---- measurement hooks ------------------------------------------------------ */

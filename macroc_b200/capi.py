@@ -108,7 +108,7 @@ def lib():
     L.macroc_assembly_res.argtypes = [vp, dp]
     L.macroc_homogenize.argtypes = [vp]
     L.macroc_gp_arrays.argtypes = [vp, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
-                                   C.POINTER(C.c_int64)]
+                                   C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     L.macroc_set_gp_data.argtypes = [vp, C.c_void_p, C.c_void_p]
     L.macroc_assembly_jac.argtypes = [vp]
     L.macroc_solve_Ax.argtypes = [vp, ip, dp]
@@ -293,10 +293,10 @@ class MacroC:
         self._chk(self._L.macroc_homogenize(self._h))
 
     def gp_arrays(self):
-        """Device pointers (ints) of strain, stress, ctan and the number of Gauss points."""
-        a, b, c, n = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_int64()
-        self._chk(self._L.macroc_gp_arrays(self._h, C.byref(a), C.byref(b), C.byref(c), C.byref(n)))
-        return a.value, b.value, c.value, n.value
+        """Device pointers (ints) of strain, stress, ctan, the number of Gauss points and the SoA pitch."""
+        a, b, c, n, pitch = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_int64(), C.c_int64()
+        self._chk(self._L.macroc_gp_arrays(self._h, C.byref(a), C.byref(b), C.byref(c), C.byref(n), C.byref(pitch)))
+        return a.value, b.value, c.value, n.value, pitch.value
 
     def set_gp_data(self, stress: np.ndarray | None = None, ctan: np.ndarray | None = None):
         s = np.ascontiguousarray(stress, dtype=np.float64) if stress is not None else None

@@ -2,9 +2,10 @@
 //
 // These are the general form of the reference's element loops
 // (src/assembly.c:85-108 and :142-162): every Gauss point has its own stress
-// (6 doubles) and tangent (36 doubles, row-major) at gpi = ie*8 + gp
-// (assembly.c:58,91,148) -- the arrays a constitutive plug-in in MicroPP's role
-// fills on the device.  With the homogenised linear law they are filled by
+// (6 doubles) and tangent (36 doubles, row-major) -- the reference's
+// gpi = ie*8 + gp data (assembly.c:58,91,148), kept on the device as SoA over
+// elements (see k_strain_stress) -- the arrays a constitutive plug-in in
+// MicroPP's role fills on the device.  With the homogenised linear law they are filled by
 // k_homogenize_linear (stress = D strain, ctan = D); with MACROC_MAT_UNIFORM the
 // same kernels take D from constant memory and never touch the arrays.
 //
@@ -29,22 +30,31 @@ struct ElemRange {
     int ezs;          // first element layer stored (global z index)
     int nez_ext;      // stored layers: owned ones plus the upper neighbour's first layer
     int64_t nex, ney; // elements per row / rows per layer
+    int64_t ne_ext;   // stored elements = pitch of the SoA Gauss-point arrays
 };
 
-// MicroPP stand-in on the device: sigma = D eps, C = D for every Gauss point.
-__global__ void k_homogenize_linear(int64_t ngp, const double *__restrict__ strain, double *__restrict__ stress,
-                                    double *__restrict__ ctan)
+// MicroPP stand-in on the device: sigma = D eps, C = D for every Gauss point of the owned
+// elements (SoA arrays, pitch ne_ext).
+__global__ void k_homogenize_linear(int64_t ne, int64_t ne_ext, const double *__restrict__ strain,
+                                    double *__restrict__ stress, double *__restrict__ ctan)
 {
-    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t < ngp * 6) {
-        int64_t gpi = t / 6; int i = (int)(t % 6);
-        double s = 0.;
+    int64_t ie = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ie >= ne) return;
+#pragma unroll 1
+    for (int gp = 0; gp < 8; ++gp) {
+        double e[6];
 #pragma unroll
-        for (int j = 0; j < 6; ++j) s = fma(c_D[i * 6 + j], strain[gpi * 6 + j], s);
-        stress[t] = s;
+        for (int j = 0; j < 6; ++j) e[j] = strain[(gp * 6 + j) * ne_ext + ie];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            double s = 0.;
+#pragma unroll
+            for (int j = 0; j < 6; ++j) s = fma(c_D[i * 6 + j], e[j], s);
+            stress[(gp * 6 + i) * ne_ext + ie] = s;
+        }
+#pragma unroll
+        for (int q = 0; q < 36; ++q) ctan[(gp * 36 + q) * ne_ext + ie] = c_D[q];
     }
-    if (ctan)
-        for (int64_t q = t; q < ngp * 36; q += (int64_t)gridDim.x * blockDim.x) ctan[q] = c_D[q % 36];
 }
 
 // pass 1: be[24] of every stored element in layers [l0, l0+nl) of the range -> scratch[q][e_local]
@@ -62,13 +72,13 @@ k_elem_forces(GridDev g, ElemRange er, int l0, int nl, double wg, const double *
     for (int q = 0; q < 24; ++q) be[q] = 0.;
     double ue[8][3];
     if (!PER_GP) gather_element(u, g, g.G + ei + (int64_t)g.NX * ej + g.npl * (er.ezs + el - g.zs), ue);
-    const double *sg = PER_GP ? stress_gp + ((int64_t)el * per_layer + (e % per_layer)) * 48 : nullptr;
+    const double *sg = PER_GP ? stress_gp + ((int64_t)el * per_layer + (e % per_layer)) : nullptr;
 #pragma unroll 1
     for (int gp = 0; gp < 8; ++gp) {
         double sig[6];
         if (PER_GP) {
 #pragma unroll
-            for (int q = 0; q < 6; ++q) sig[q] = __ldg(sg + gp * 6 + q);
+            for (int q = 0; q < 6; ++q) sig[q] = __ldg(sg + (gp * 6 + q) * er.ne_ext);
         } else {
             double eps[6];
             element_strain(ue, gp, eps);
@@ -160,28 +170,39 @@ k_assemble_elements(GridDev g, ElemRange er, double wg, const double *__restrict
 #pragma unroll
             for (int q = 0; q < 24; ++q) blk[d][q] = 0.;
         if (exists) {
-            const double *cg = PER_GP ? ctan_gp + ((int64_t)(ek - er.ezs) * per_layer + ei + er.nex * (int64_t)ej) * 288 : nullptr;
+            const double *cg = PER_GP ? ctan_gp + ((int64_t)(ek - er.ezs) * per_layer + ei + er.nex * (int64_t)ej) : nullptr;
 #pragma unroll 1
             for (int gp = 0; gp < 8; ++gp) {
-                double C[36];
-#pragma unroll
-                for (int q = 0; q < 36; ++q) C[q] = PER_GP ? __ldg(cg + gp * 36 + q) : c_D[q];
                 const double hx = c_dsh[gp][a][0], hy = c_dsh[gp][a][1], hz = c_dsh[gp][a][2];
-                double T[3][6];                         // rows 3a..3a+2 of B^T C
+                // stream the tangent one column k at a time: T[d] = (B_a^T C)[d][k] * wg, then every
+                // block column b takes T[d] * B_b[k][.]  (B has at most two non-zeros per (k, b))
 #pragma unroll
-                for (int l = 0; l < 6; ++l) {
-                    T[0][l] = hx * C[0 * 6 + l] + hy * C[3 * 6 + l] + hz * C[4 * 6 + l];
-                    T[1][l] = hy * C[1 * 6 + l] + hx * C[3 * 6 + l] + hz * C[5 * 6 + l];
-                    T[2][l] = hz * C[2 * 6 + l] + hx * C[4 * 6 + l] + hy * C[5 * 6 + l];
-                }
+                for (int k = 0; k < 6; ++k) {
+                    double ck[6];
 #pragma unroll
-                for (int b = 0; b < 8; ++b) {
-                    const double bx = c_dsh[gp][b][0] * wg, by = c_dsh[gp][b][1] * wg, bz = c_dsh[gp][b][2] * wg;
+                    for (int r = 0; r < 6; ++r) ck[r] = PER_GP ? __ldg(cg + (int64_t)(gp * 36 + r * 6 + k) * er.ne_ext) : c_D[r * 6 + k];
+                    const double T0 = (hx * ck[0] + hy * ck[3] + hz * ck[4]) * wg;
+                    const double T1 = (hy * ck[1] + hx * ck[3] + hz * ck[5]) * wg;
+                    const double T2 = (hz * ck[2] + hx * ck[4] + hy * ck[5]) * wg;
 #pragma unroll
-                    for (int d = 0; d < 3; ++d) {
-                        blk[d][3 * b + 0] += T[d][0] * bx + T[d][3] * by + T[d][4] * bz;
-                        blk[d][3 * b + 1] += T[d][1] * by + T[d][3] * bx + T[d][5] * bz;
-                        blk[d][3 * b + 2] += T[d][2] * bz + T[d][4] * bx + T[d][5] * by;
+                    for (int b = 0; b < 8; ++b) {
+                        const double bx = c_dsh[gp][b][0], by = c_dsh[gp][b][1], bz = c_dsh[gp][b][2];
+                        // column 3b+c of B: row k non-zero for (k,c) in {(0,0),(1,1),(2,2),(3,0)=by,(3,1)=bx,(4,0)=bz,(4,2)=bx,(5,1)=bz,(5,2)=by}
+                        if (k == 0) { blk[0][3 * b + 0] = fma(T0, bx, blk[0][3 * b + 0]); blk[1][3 * b + 0] = fma(T1, bx, blk[1][3 * b + 0]); blk[2][3 * b + 0] = fma(T2, bx, blk[2][3 * b + 0]); }
+                        if (k == 1) { blk[0][3 * b + 1] = fma(T0, by, blk[0][3 * b + 1]); blk[1][3 * b + 1] = fma(T1, by, blk[1][3 * b + 1]); blk[2][3 * b + 1] = fma(T2, by, blk[2][3 * b + 1]); }
+                        if (k == 2) { blk[0][3 * b + 2] = fma(T0, bz, blk[0][3 * b + 2]); blk[1][3 * b + 2] = fma(T1, bz, blk[1][3 * b + 2]); blk[2][3 * b + 2] = fma(T2, bz, blk[2][3 * b + 2]); }
+                        if (k == 3) {
+                            blk[0][3 * b + 0] = fma(T0, by, blk[0][3 * b + 0]); blk[1][3 * b + 0] = fma(T1, by, blk[1][3 * b + 0]); blk[2][3 * b + 0] = fma(T2, by, blk[2][3 * b + 0]);
+                            blk[0][3 * b + 1] = fma(T0, bx, blk[0][3 * b + 1]); blk[1][3 * b + 1] = fma(T1, bx, blk[1][3 * b + 1]); blk[2][3 * b + 1] = fma(T2, bx, blk[2][3 * b + 1]);
+                        }
+                        if (k == 4) {
+                            blk[0][3 * b + 0] = fma(T0, bz, blk[0][3 * b + 0]); blk[1][3 * b + 0] = fma(T1, bz, blk[1][3 * b + 0]); blk[2][3 * b + 0] = fma(T2, bz, blk[2][3 * b + 0]);
+                            blk[0][3 * b + 2] = fma(T0, bx, blk[0][3 * b + 2]); blk[1][3 * b + 2] = fma(T1, bx, blk[1][3 * b + 2]); blk[2][3 * b + 2] = fma(T2, bx, blk[2][3 * b + 2]);
+                        }
+                        if (k == 5) {
+                            blk[0][3 * b + 1] = fma(T0, bz, blk[0][3 * b + 1]); blk[1][3 * b + 1] = fma(T1, bz, blk[1][3 * b + 1]); blk[2][3 * b + 1] = fma(T2, bz, blk[2][3 * b + 1]);
+                            blk[0][3 * b + 2] = fma(T0, by, blk[0][3 * b + 2]); blk[1][3 * b + 2] = fma(T1, by, blk[1][3 * b + 2]); blk[2][3 * b + 2] = fma(T2, by, blk[2][3 * b + 2]);
+                        }
                     }
                 }
             }

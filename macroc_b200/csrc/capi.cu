@@ -56,6 +56,7 @@ struct macroc_ctx {
     CgScalars *sc_host = nullptr;    // pinned [2]
     double *stage = nullptr;         // device staging, 3*nloc doubles (boundary layout)
     double *strain = nullptr, *stress = nullptr, *ctan = nullptr;   // Gauss-point arrays, gpi = ie*8+gp
+    double *gp_halo = nullptr;       // send/recv staging of one element layer of a Gauss-point array
     double *scratch = nullptr;       // element forces of one z-chunk, SoA over elements
     int chunk_planes = 0;
     ElemRange er;
@@ -259,7 +260,7 @@ static int ctx_free(macroc_ctx *c)
     for (int i = 0; i < V_COUNT; ++i) cudaFree(c->vec[i]);
     cudaFree(c->A); cudaFree(c->Ke); cudaFree(c->T); cudaFree(c->nodemask); cudaFree(c->bc_idx); cudaFree(c->bc_coef);
     cudaFree(c->partial); cudaFree(c->sums); cudaFree(c->sc); cudaFree(c->stage); cudaFree(c->strain); cudaFree(c->stress);
-    cudaFree(c->ctan); cudaFree(c->scratch); cudaFree(c->consts);
+    cudaFree(c->ctan); cudaFree(c->scratch); cudaFree(c->consts); cudaFree(c->gp_halo);
     if (c->device >= 0 && c->device < 64 && g_const_owner[c->device] == c->id) g_const_owner[c->device] = 0;
     cudaFree(c->flush);
     if (c->sums_host) cudaFreeHost(c->sums_host);
@@ -334,6 +335,7 @@ extern "C" int macroc_create(const macroc_config *cfg, int rank, int nranks, con
     c->er.nez_ext = slab.nez + (slab.has_upper() ? 1 : 0);
     c->ne_owned = (int64_t)slab.nex * slab.ney * slab.nez;
     c->ne_ext = (int64_t)slab.nex * slab.ney * c->er.nez_ext;
+    c->er.ne_ext = std::max<int64_t>(c->ne_ext, 1);
     {
         // residual scratch: 24 doubles per element of a chunk of node planes (<= ~256 MB)
         int64_t per_layer = std::max<int64_t>((int64_t)slab.nex * slab.ney, 1);
@@ -469,16 +471,22 @@ static int ensure_gp_arrays(macroc_ctx *c, bool need_ctan)
 }
 
 // Gauss-point halo: the first owned element layer of rank r+1 is the layer above rank r's
-// top node plane; rank r keeps a copy behind its owned layers (layer index nez).
-static int halo_gp_layer(macroc_ctx *c, double *arr, int doubles_per_elem)
+// top node plane; rank r keeps a copy behind its owned layers (layer index nez).  The arrays
+// are SoA over elements, so a layer is packed into / unpacked from a contiguous buffer.
+static int halo_gp_layer(macroc_ctx *c, double *arr, int nq)
 {
     if (!c->comm) return MACROC_OK;
     const Slab &s = c->slab;
-    size_t cnt = (size_t)s.nex * s.ney * doubles_per_elem;
+    const int64_t per_layer = (int64_t)s.nex * s.ney;
+    const size_t cnt = (size_t)per_layer * nq;
+    if (!c->gp_halo) CU(c, cudaMalloc(&c->gp_halo, sizeof(double) * 2 * (size_t)per_layer * 288));
+    double *sbuf = c->gp_halo, *rbuf = c->gp_halo + (size_t)per_layer * 288;
+    if (s.has_lower()) LAUNCH(c, k_gp_layer_copy, cdiv64(cnt, 256), 256, nq, per_layer, c->er.ne_ext, (int64_t)0, arr, sbuf, 1);
     NC(c, ncclGroupStart());
-    if (s.has_lower()) NC(c, ncclSend(arr, cnt, ncclDouble, s.rank - 1, c->comm, c->stream));
-    if (s.has_upper()) NC(c, ncclRecv(arr + (size_t)c->ne_owned * doubles_per_elem, cnt, ncclDouble, s.rank + 1, c->comm, c->stream));
+    if (s.has_lower()) NC(c, ncclSend(sbuf, cnt, ncclDouble, s.rank - 1, c->comm, c->stream));
+    if (s.has_upper()) NC(c, ncclRecv(rbuf, cnt, ncclDouble, s.rank + 1, c->comm, c->stream));
     NC(c, ncclGroupEnd());
+    if (s.has_upper()) LAUNCH(c, k_gp_layer_copy, cdiv64(cnt, 256), 256, nq, per_layer, c->er.ne_ext, c->ne_owned, arr, rbuf, 0);
     return MACROC_OK;
 }
 
@@ -494,7 +502,7 @@ extern "C" int macroc_set_strains(macroc_ctx *c, int materialize)
         if ((rc = ensure_gp_arrays(c, false))) return rc;
         // strain of the owned elements; stress = D strain as a by-product for the uniform law
         if (c->ne_owned > 0)
-            LAUNCH(c, k_strain_stress, cdiv64(c->ne_owned, 128), 128, c->g, s.ezs, s.nez, c->vec[V_U], c->strain,
+            LAUNCH(c, k_strain_stress, cdiv64(c->ne_owned, 128), 128, c->g, s.ezs, s.nez, c->er.ne_ext, c->vec[V_U], c->strain,
                    c->cfg.material == MACROC_MAT_PER_GP ? nullptr : c->stress);
         CU(c, cudaGetLastError());
     }
@@ -509,16 +517,13 @@ extern "C" int macroc_homogenize(macroc_ctx *c)
     { int _rc = bind_constants(c); if (_rc) return _rc; }
     int rc = ensure_gp_arrays(c, true);
     if (rc) return rc;
-    int64_t ngp = c->ne_owned * 8;
-    if (ngp > 0) LAUNCH(c, k_homogenize_linear, (int)std::min<int64_t>(cdiv64(ngp * 6, 256), 148 * 16), 256, ngp, c->strain, c->stress, c->ctan);
-    // grid-stride part covers ctan; the stress part needs one thread per value
-    if (ngp * 6 > (int64_t)148 * 16 * 256)
-        LAUNCH(c, k_homogenize_linear, cdiv64(ngp * 6, 256), 256, ngp, c->strain, c->stress, (double *)nullptr);
+    if (c->ne_owned > 0) LAUNCH(c, k_homogenize_linear, cdiv64(c->ne_owned, 128), 128, c->ne_owned, c->er.ne_ext, c->strain, c->stress, c->ctan);
     CU(c, cudaGetLastError());
     return MACROC_OK;
 }
 
-extern "C" int macroc_gp_arrays(macroc_ctx *c, double **strain, double **stress, double **ctan, int64_t *n_gp)
+extern "C" int macroc_gp_arrays(macroc_ctx *c, double **strain, double **stress, double **ctan, int64_t *n_gp,
+                                int64_t *pitch)
 {
     if (!c) return MACROC_ERR_ARG;
     CU(c, cudaSetDevice(c->device));
@@ -528,6 +533,38 @@ extern "C" int macroc_gp_arrays(macroc_ctx *c, double **strain, double **stress,
     if (stress) *stress = c->stress;
     if (ctan) *ctan = c->ctan;
     if (n_gp) *n_gp = c->ne_owned * 8;
+    if (pitch) *pitch = c->er.ne_ext;
+    return MACROC_OK;
+}
+
+// host (reference AoS view, gpi = ie*8+gp) -> device SoA arrays
+static int gp_upload(macroc_ctx *c, const double *host, double *dev, int n)
+{
+    const int64_t ne = c->ne_owned;
+    if (!host || ne == 0) return MACROC_OK;
+    double *tmp = nullptr;
+    CU(c, cudaMalloc(&tmp, sizeof(double) * 8 * n * (size_t)ne));
+    cudaError_t e = cudaMemcpyAsync(tmp, host, sizeof(double) * 8 * n * (size_t)ne, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) {
+        LAUNCH(c, k_gp_aos_soa, cdiv64(ne * 8 * n, 256), 256, n, ne, c->er.ne_ext, tmp, dev, 1);
+        e = cudaStreamSynchronize(c->stream);
+    }
+    cudaFree(tmp);
+    if (e != cudaSuccess) FAIL(c, MACROC_ERR_CUDA, "gp_upload: %s", cudaGetErrorString(e));
+    return MACROC_OK;
+}
+
+static int gp_download(macroc_ctx *c, const double *dev, double *host, int n)
+{
+    const int64_t ne = c->ne_owned;
+    if (!host || ne == 0) return MACROC_OK;
+    double *tmp = nullptr;
+    CU(c, cudaMalloc(&tmp, sizeof(double) * 8 * n * (size_t)ne));
+    LAUNCH(c, k_gp_aos_soa, cdiv64(ne * 8 * n, 256), 256, n, ne, c->er.ne_ext, dev, tmp, 0);
+    cudaError_t e = cudaMemcpyAsync(host, tmp, sizeof(double) * 8 * n * (size_t)ne, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(tmp);
+    if (e != cudaSuccess) FAIL(c, MACROC_ERR_CUDA, "gp_download: %s", cudaGetErrorString(e));
     return MACROC_OK;
 }
 
@@ -537,9 +574,8 @@ extern "C" int macroc_set_gp_data(macroc_ctx *c, const double *stress_host, cons
     CU(c, cudaSetDevice(c->device));
     int rc = ensure_gp_arrays(c, ctan_host != nullptr);
     if (rc) return rc;
-    if (stress_host && c->ne_owned) CU(c, cudaMemcpyAsync(c->stress, stress_host, sizeof(double) * 48 * c->ne_owned, cudaMemcpyHostToDevice, c->stream));
-    if (ctan_host && c->ne_owned) CU(c, cudaMemcpyAsync(c->ctan, ctan_host, sizeof(double) * 288 * c->ne_owned, cudaMemcpyHostToDevice, c->stream));
-    CU(c, cudaStreamSynchronize(c->stream));
+    if ((rc = gp_upload(c, stress_host, c->stress, 6))) return rc;
+    if ((rc = gp_upload(c, ctan_host, c->ctan, 36))) return rc;
     return MACROC_OK;
 }
 
@@ -551,7 +587,7 @@ static int residual_launch(macroc_ctx *c, int *nparts_out)
     const bool per_gp = c->cfg.material == MACROC_MAT_PER_GP;
     if (per_gp) {
         if (!c->stress) FAIL(c, MACROC_ERR_ARG, "assembly_res: no Gauss-point stresses (call set_strains + homogenize)");
-        int rc = halo_gp_layer(c, c->stress, 48);
+        int rc = halo_gp_layer(c, c->stress, 48);   // 8 gp x 6
         if (rc) return rc;
     }
     int nparts = 0;
@@ -619,7 +655,7 @@ extern "C" int macroc_assembly_jac(macroc_ctx *c)
         if (per_gp || c->cfg.jac_mode == MACROC_JAC_ELEMENT) {
             if (per_gp) {
                 if (!c->ctan) FAIL(c, MACROC_ERR_ARG, "assembly_jac: no Gauss-point tangents (call homogenize)");
-                if ((rc = halo_gp_layer(c, c->ctan, 288))) return rc;
+                if ((rc = halo_gp_layer(c, c->ctan, 288))) return rc;   // 8 gp x 36
             }
             const int smem = TILE_DOUBLES * (int)sizeof(double) + 27 * 32;
             static bool configured = false;
@@ -911,7 +947,8 @@ extern "C" int macroc_calc_force(macroc_ctx *c, double *force)
         int nblk = cdiv64(count, 128);
         LAUNCH(c, k_force, nblk, 128, c->g, s.ezs, s.nez, c->cfg.bc_type, c->geo.dx, c->geo.dy, c->geo.dz, c->cfg.lx,
                c->cfg.lz, c->geo.rad, c->vec[V_U],
-               (c->cfg.material == MACROC_MAT_PER_GP && c->stress) ? c->stress : (const double *)nullptr, c->partial);
+               (c->cfg.material == MACROC_MAT_PER_GP && c->stress) ? c->stress : (const double *)nullptr, c->er.ne_ext,
+               c->partial);
         LAUNCH(c, k_reduce, 1, 256, c->partial, nblk, c->sums);
     } else
         CU(c, cudaMemsetAsync(c->sums, 0, sizeof(double), c->stream));
@@ -1041,10 +1078,9 @@ extern "C" int macroc_get_strain_stress(macroc_ctx *c, double *strain, double *s
     int64_t ne = c->ne_owned;
     if (n_gp) *n_gp = ne * 8;
     if ((strain || stress) && !c->strain && ne > 0) FAIL(c, MACROC_ERR_ARG, "get_strain_stress: call set_strains(ctx, 1) first");
-    if (strain && ne > 0) CU(c, cudaMemcpyAsync(strain, c->strain, sizeof(double) * 48 * ne, cudaMemcpyDeviceToHost, c->stream));
-    if (stress && ne > 0) CU(c, cudaMemcpyAsync(stress, c->stress, sizeof(double) * 48 * ne, cudaMemcpyDeviceToHost, c->stream));
-    CU(c, cudaStreamSynchronize(c->stream));
-    return MACROC_OK;
+    int rc = gp_download(c, c->strain, strain, 6);
+    if (!rc) rc = gp_download(c, c->stress, stress, 6);
+    return rc;
 }
 
 // ---------------------------------------------------------------------------

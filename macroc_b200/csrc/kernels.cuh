@@ -492,11 +492,14 @@ __device__ __forceinline__ void gather_element(const double *__restrict__ u, con
     }
 }
 
-// set_strains with materialisation: strain/stress[gpi*6 + i], gpi = ie*8 + gp
-// (assembly.c:58), ie the rank-local element in DMDAGetElements order.
+// set_strains with materialisation.  Device layout of the Gauss-point arrays is SoA over the
+// rank's stored elements (coalesced for every kernel that walks elements with consecutive
+// lanes):  strain/stress[(gp*6 + i)*ne_ext + ie],  ctan[((gp*6 + k)*6 + l)*ne_ext + ie],
+// ie = rank-local element in DMDAGetElements order.  The reference's gpi = ie*8+gp AoS view
+// (assembly.c:58,91,148) is what the host-facing copies of the C ABI speak (k_gp_aos_soa).
 __global__ void __launch_bounds__(128)
-k_strain_stress(GridDev g, int ezs, int nez, const double *__restrict__ u, double *__restrict__ strain,
-                double *__restrict__ stress)
+k_strain_stress(GridDev g, int ezs, int nez, int64_t ne_ext, const double *__restrict__ u,
+                double *__restrict__ strain, double *__restrict__ stress)
 {
     int64_t ie = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int64_t nex = g.NX - 1, ney = g.NY - 1;
@@ -512,17 +515,44 @@ k_strain_stress(GridDev g, int ezs, int nez, const double *__restrict__ u, doubl
         stress_of(eps, sig);
 #pragma unroll
         for (int q = 0; q < 6; ++q) {
-            strain[(ie * 8 + gp) * 6 + q] = eps[q];
-            if (stress) stress[(ie * 8 + gp) * 6 + q] = sig[q];
+            strain[(gp * 6 + q) * ne_ext + ie] = eps[q];
+            if (stress) stress[(gp * 6 + q) * ne_ext + ie] = sig[q];
         }
     }
+}
+
+// AoS (gpi-major, [ie][gp][n]) <-> SoA ([(gp*n + i)][ie], pitch ne_ext) for n = 6 or 36
+__global__ void k_gp_aos_soa(int n, int64_t ne, int64_t ne_ext, const double *__restrict__ in, double *__restrict__ out,
+                             int to_soa)
+{
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ne * 8 * n) return;
+    if (to_soa) {           // t indexes the SoA side: coalesced writes
+        int64_t ie = t % ne, q = t / ne;
+        out[q * ne_ext + ie] = in[ie * 8 * n + q];
+    } else {                // t indexes the SoA side: coalesced reads
+        int64_t ie = t % ne, q = t / ne;
+        out[ie * 8 * n + q] = in[q * ne_ext + ie];
+    }
+}
+
+// one element layer of a SoA Gauss-point array <-> contiguous buffer (Gauss-point halo)
+__global__ void k_gp_layer_copy(int nq, int64_t per_layer, int64_t ne_ext, int64_t layer_off, double *__restrict__ arr,
+                                double *__restrict__ buf, int pack)
+{
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= per_layer * nq) return;
+    int64_t x = t % per_layer, q = t / per_layer;
+    if (pack) buf[t] = arr[q * ne_ext + layer_off + x];
+    else arr[q * ne_ext + layer_off + x] = buf[t];
 }
 
 // forces.c:58-106 / :115-166: sum of the 8 Gauss-point stresses of the elements
 // next to the loaded boundary, component [3]*dy*dz (bending) or [1]*dx*dz (circle).
 __global__ void __launch_bounds__(128)
 k_force(GridDev g, int ezs, int nez, int bc_type, double dx, double dy, double dz, double lx, double lz,
-        double rad, const double *__restrict__ u, const double *__restrict__ stress_gp, double *__restrict__ partial)
+        double rad, const double *__restrict__ u, const double *__restrict__ stress_gp, int64_t ne_ext,
+        double *__restrict__ partial)
 {
     __shared__ double sm[4];
     int64_t nex = g.NX - 1, ney = g.NY - 1;
@@ -546,7 +576,7 @@ k_force(GridDev g, int ezs, int nez, int bc_type, double dx, double dy, double d
             const int comp = bc_type == 0 ? 3 : 1;
             if (stress_gp) {                      // Gauss-point stresses of the material plug-in (forces.c:85,149)
                 const int64_t e = ei + nex * (ej + ney * (int64_t)(ek - ezs));
-                for (int gp = 0; gp < 8; ++gp) ave += stress_gp[(e * 8 + gp) * 6 + comp];
+                for (int gp = 0; gp < 8; ++gp) ave += stress_gp[(gp * 6 + comp) * ne_ext + e];
             } else {
                 int64_t base = g.G + ei + (int64_t)g.NX * ej + g.npl * (ek - g.zs);
                 double ue[8][3];

@@ -311,3 +311,33 @@ def test_force_from_plugin_stresses():
     dy, dz = 1.0 / 3, 50.0 / 4
     expect = sum(stress[(6 - 2) + ey * 5 + ez * 15, :, 3].sum() * dy * dz for ey in range(3) for ez in range(4))
     assert m.calc_force() == pytest.approx(expect, rel=1e-12)
+
+
+def test_gpu_material_model_writes_device_arrays_in_place():
+    """The plug-in contract of macroc_gp_arrays: a GPU material model (here torch, standing in for
+    a CUDA kernel of the caller) reads the SoA strain array and writes stress and ctan in place."""
+    import torch
+    kw = dict(NX=8, NY=5, NZ=6, bc_type=M.BC_BENDING)
+    m = M.MacroC(M.Config(material=M.MAT_PER_GP, device=0, **kw))
+    o = O.Oracle(O.Config(faithful_ke=0, **kw))
+    u0 = 1e-3 * np.random.default_rng(4).standard_normal(o.ndof)
+    o.set_vec("u", u0); m.set_vec(M.VEC_U, u0)
+    o.set_strains(); o.homogenize(); m.set_strains()
+    p_eps, p_sig, p_ct, ngp, pitch = m.gp_arrays()
+    ne = ngp // 8
+
+    def view(ptr, nq):
+        # wrap the library's device memory without copying
+        class _W:
+            __cuda_array_interface__ = {"shape": (nq * pitch,), "typestr": "<f8", "data": (ptr, False), "version": 2}
+        return torch.as_tensor(_W(), device="cuda:0").view(nq, pitch)
+
+    eps, sig, ct = view(p_eps, 48), view(p_sig, 48), view(p_ct, 288)
+    D = torch.tensor(O.isotropic_D(), device="cuda:0")
+    e = eps[:, :ne].view(8, 6, ne)
+    sig[:, :ne] = torch.einsum("ij,gje->gie", D, e).reshape(48, ne)          # sigma = D eps, in place
+    ct[:, :ne] = D.reshape(1, 36, 1).expand(8, 36, ne).reshape(288, ne)
+    torch.cuda.synchronize()
+    assert m.assembly_res() == pytest.approx(o.assembly_res(), rel=1e-12)
+    o.assembly_jac(); m.assembly_jac()
+    assert rel_err(m.get_matrix_blocks(), o.block_stencil()) < TOL_MAT
