@@ -68,7 +68,8 @@ struct macroc_ctx {
     int vec_blocks = 0, spmv_blocks = 0;
     cudaGraphExec_t cg_graph[2] = {nullptr, nullptr};   // `check` PCG iterations per launch, per operator
     uint64_t cg_graph_launches[2] = {0, 0};
-    int spmv_variant = 10;           // 10: TMA ring 8 warps x 4 stages (default); 0/1: per-lane LDG; see spmv_launch
+    int spmv_variant = 10;           // 10: TMA ring 8 warps x 4 stages (default); 11: 8x5, 14: 6x6; 0: per-lane LDG
+                                     // (kept for A/B measurements, tools/spmv_sweep.py; MACROC_SPMV_VARIANT)
     cudaEvent_t ev_user[8] = {nullptr};
     // live profile of the operator application (ring of event pairs)
     static constexpr int PROF_RING = 128;
@@ -703,17 +704,7 @@ static int spmv_launch(macroc_ctx *c, double *p, double *w, int64_t first, int64
     switch (c->spmv_variant) {
         case 10: return spmv_launch_tma<8, 4>(c, p, w, first, count, partial, with_dot, done);
         case 11: return spmv_launch_tma<8, 5>(c, p, w, first, count, partial, with_dot, done);
-        case 12: return spmv_launch_tma<4, 8>(c, p, w, first, count, partial, with_dot, done);
-        case 13: return spmv_launch_tma<4, 12>(c, p, w, first, count, partial, with_dot, done);
         case 14: return spmv_launch_tma<6, 6>(c, p, w, first, count, partial, with_dot, done);
-        case 15: return spmv_launch_tma<4, 4>(c, p, w, first, count, partial, with_dot, done);
-        case 16: return spmv_launch_tma<12, 4>(c, p, w, first, count, partial, with_dot, done);
-        case 1: {
-            int blocks = (int)std::min<int64_t>(cdiv64(count, 8), 148 * 8);
-            if (with_dot) LAUNCH(c, (k_spmv<true, 4>), blocks, 256, g, c->A, p, w, first, count, partial, done);
-            else LAUNCH(c, (k_spmv<false, 4>), blocks, 256, g, c->A, p, w, first, count, partial, done);
-            return blocks;
-        }
         default: {
             int blocks = (int)std::min<int64_t>(cdiv64(count, 8), 148 * 8);
             if (with_dot) LAUNCH(c, (k_spmv<true, 1>), blocks, 256, g, c->A, p, w, first, count, partial, done);

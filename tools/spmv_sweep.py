@@ -9,7 +9,7 @@ sys.path.insert(0, ".")
 import macroc_b200 as M
 
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 256
-variants = [int(v) for v in sys.argv[2].split(",")] if len(sys.argv) > 2 else [0, 1, 10, 11, 12, 13, 14, 15, 16]
+variants = [int(v) for v in sys.argv[2].split(",")] if len(sys.argv) > 2 else [0, 10, 11, 14]
 nd = 3 * N ** 3
 nb = (3 * N - 2) ** 3
 bytes_spmv = 72 * nb + 16 * nd
