@@ -59,6 +59,8 @@ typedef struct {
     double  lx, ly, lz;            /* -lx -ly -lz             (macroc.h:47-49: 50, 1, 50)   */
     int32_t bc_type;               /* -bc_type                (init.c:64: BC_CIRCLE)        */
     int32_t ts;                    /* -ts                     (macroc.h:41: 1)              */
+    int32_t vtu_freq;              /* -vtu_freq               (macroc.h:42: -1 = never)     */
+    int32_t pad0;
     double  dt, final_time;        /* -dt                     (macroc.h:43,40)              */
     int32_t newton_max_its;        /* -newton_max_its | -new_its (macroc.h:38: 5)           */
     double  newton_min_tol;        /* -newton_min_tol | -new_tol (macroc.h:37: 1e-1)        */
@@ -160,6 +162,12 @@ int macroc_get_matrix_blocks(macroc_ctx *ctx, double *host);
 int macroc_matmult(macroc_ctx *ctx, int op, const double *x_host, double *y_host);
 /* Gauss-point strain / stress in the reference's AoS view ([gpi*6 + i], gpi = ie*8+gp) */
 int macroc_get_strain_stress(macroc_ctx *ctx, double *strain, double *stress, int64_t *n_gp);
+
+/* write_pvtu (src/output.c:25-267): <prefix>.pvtu (rank 0) and <prefix>-subdo-<rank>.vtu with the
+ * ghosted box's points, the rank's hex cells (type 12, local ghosted numbering), displ, part,
+ * cost / non-linear (0: no MicroPP) and the element integrals of strain and stress
+ * (sum_gp value*wg, output.c:230,247), same ASCII formats as the reference. */
+int macroc_write_pvtu(macroc_ctx *ctx, const char *file_prefix);
 
 /* ---- measurement hooks ------------------------------------------------------ */
 /* Runs `reps` launches of one kernel family on the context's stream with data

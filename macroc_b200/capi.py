@@ -35,7 +35,7 @@ EXPORTS = [
     "macroc_get_vec", "macroc_get_matrix_blocks", "macroc_matmult", "macroc_get_strain_stress",
     "macroc_time_kernel", "macroc_launch_count", "macroc_device_synchronize", "macroc_version",
     "macroc_event_record", "macroc_event_elapsed_ms", "macroc_profile_enable", "macroc_profile_get",
-    "macroc_homogenize", "macroc_gp_arrays", "macroc_set_gp_data", "macroc_set_operator",
+    "macroc_homogenize", "macroc_gp_arrays", "macroc_set_gp_data", "macroc_set_operator", "macroc_write_pvtu",
 ]
 
 
@@ -50,7 +50,7 @@ class CConfig(C.Structure):
         ("NX", C.c_int32), ("NY", C.c_int32), ("NZ", C.c_int32),
         ("px", C.c_int32), ("py", C.c_int32), ("pz", C.c_int32),
         ("lx", C.c_double), ("ly", C.c_double), ("lz", C.c_double),
-        ("bc_type", C.c_int32), ("ts", C.c_int32),
+        ("bc_type", C.c_int32), ("ts", C.c_int32), ("vtu_freq", C.c_int32), ("pad0", C.c_int32),
         ("dt", C.c_double), ("final_time", C.c_double),
         ("newton_max_its", C.c_int32),
         ("newton_min_tol", C.c_double), ("newton_rel_tol", C.c_double),
@@ -114,6 +114,7 @@ def lib():
     L.macroc_solve_Ax.argtypes = [vp, ip, dp]
     L.macroc_ksp_reason.argtypes = [vp, ip]
     L.macroc_set_operator.argtypes = [vp, C.c_int]
+    L.macroc_write_pvtu.argtypes = [vp, C.c_char_p]
     L.macroc_update_u.argtypes = [vp]
     L.macroc_calc_B.argtypes = [C.c_int, dp]
     L.macroc_calc_force.argtypes = [vp, dp]
@@ -311,6 +312,9 @@ class MacroC:
         its, rn = C.c_int(), C.c_double()
         self._chk(self._L.macroc_solve_Ax(self._h, C.byref(its), C.byref(rn)))
         return its.value, rn.value
+
+    def write_pvtu(self, file_prefix: str):
+        self._chk(self._L.macroc_write_pvtu(self._h, file_prefix.encode()))
 
     def set_operator(self, op: int):
         self._chk(self._L.macroc_set_operator(self._h, op))

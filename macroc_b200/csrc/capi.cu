@@ -141,6 +141,7 @@ extern "C" int macroc_default_config(macroc_config *cfg)
     cfg->lx = 50.; cfg->ly = 1.; cfg->lz = 50.;              // macroc.h:47-49
     cfg->bc_type = MACROC_BC_CIRCLE;                         // init.c:64
     cfg->ts = 1; cfg->dt = 0.001; cfg->final_time = 1.0;     // macroc.h:40-43
+    cfg->vtu_freq = -1;                                      // macroc.h:42
     cfg->newton_max_its = 5; cfg->newton_min_tol = 1.0e-1; cfg->newton_rel_tol = 1.0e-4;   // macroc.h:36-38
     cfg->ksp_rtol = 1.0e-5; cfg->ksp_abstol = 1.0e-50; cfg->ksp_dtol = 1.0e4; cfg->ksp_maxits = 10000;  // init.c:147-148
     cfg->E = 1.0e7; cfg->nu = 0.25;                          // init.c:31
@@ -167,6 +168,7 @@ extern "C" int macroc_config_from_args(macroc_config *cfg, int argc, const char 
         else if (is("-ly")) cfg->ly = atof(v);
         else if (is("-lz")) cfg->lz = atof(v);
         else if (is("-ts")) cfg->ts = atoi(v);
+        else if (is("-vtu_freq")) cfg->vtu_freq = atoi(v);
         else if (is("-newton_min_tol") || is("-new_tol")) cfg->newton_min_tol = atof(v);
         else if (is("-newton_rel_tol")) cfg->newton_rel_tol = atof(v);
         else if (is("-newton_max_its") || is("-new_its")) cfg->newton_max_its = atoi(v);
@@ -1072,6 +1074,131 @@ extern "C" int macroc_get_strain_stress(macroc_ctx *c, double *strain, double *s
     int rc = gp_download(c, c->strain, strain, 6);
     if (!rc) rc = gp_download(c, c->stress, stress, 6);
     return rc;
+}
+
+// write_pvtu (src/output.c:25-267).  Host-side formatting of data fetched through the same
+// device paths the solver uses; the numbers printed are computed on the GPU.
+extern "C" int macroc_write_pvtu(macroc_ctx *c, const char *file_prefix)
+{
+    if (!c || !file_prefix) return MACROC_ERR_ARG;
+    CU(c, cudaSetDevice(c->device));
+    { int _rc = bind_constants(c); if (_rc) return _rc; }
+    const Slab &s = c->slab;
+    const GridDev &g = c->g;
+    char name[4096];
+    if (s.rank == 0) {
+        snprintf(name, sizeof(name), "%s.pvtu", file_prefix);
+        FILE *fp = fopen(name, "w");
+        if (!fp) FAIL(c, 65, "write_pvtu: cannot open %s", name);
+        fprintf(fp,
+                "<?xml version=\"1.0\"?>\n"
+                "<VTKFile type=\"PUnstructuredGrid\" version=\"0.1\" byte_order=\"LittleEndian\">\n"
+                "<PUnstructuredGrid GhostLevel=\"0\">\n"
+                "<PPoints>\n"
+                "  <PDataArray type=\"Float64\" Name=\"Position\"   NumberOfComponents=\"3\"/>\n"
+                "</PPoints>\n"
+                "<PCells>\n"
+                "  <PDataArray type=\"Int32\" Name=\"connectivity\" NumberOfComponents=\"1\"/>\n"
+                "  <PDataArray type=\"Int32\" Name=\"offsets\"      NumberOfComponents=\"1\"/>\n"
+                "  <PDataArray type=\"UInt8\" Name=\"types\"        NumberOfComponents=\"1\"/>\n"
+                "</PCells>\n"
+                "<PPointData Vectors=\"displ\">\n"
+                "  <PDataArray type=\"Float64\" Name=\"displ\"      NumberOfComponents=\"3\" />\n"
+                "</PPointData>\n"
+                "<PCellData>\n"
+                "  <PDataArray type=\"Int32\"   Name=\"part\"       NumberOfComponents=\"1\"/>\n"
+                "  <PDataArray type=\"Float64\" Name=\"cost\"       NumberOfComponents=\"1\"/>\n"
+                "  <PDataArray type=\"Int32\"   Name=\"non-linear\" NumberOfComponents=\"1\"/>\n"
+                "<PDataArray type=\"Float64\" Name=\"strain\"       NumberOfComponents=\"6\"/>\n"
+                "<PDataArray type=\"Float64\" Name=\"stress\"       NumberOfComponents=\"6\"/>\n"
+                "</PCellData>\n");
+        for (int i = 0; i < s.nranks; ++i) fprintf(fp, "  <Piece Source=\"%s-subdo-%d.vtu\"/>\n", file_prefix, i);
+        fprintf(fp, "</PUnstructuredGrid>\n</VTKFile>\n");
+        fclose(fp);
+    }
+    // ghosted displacement (DMGlobalToLocal, output.c:150-153) and Gauss-point strain / stress
+    int rc = halo_exchange(c, c->vec[V_U], c->stream);
+    if (rc) return rc;
+    const int64_t N = g.npl * s.Zm, node0 = (int64_t)(s.Zs - s.zs) * g.npl;
+    std::vector<double> u_loc((size_t)3 * N);
+    {
+        double *tmp = nullptr;
+        CU(c, cudaMalloc(&tmp, sizeof(double) * 3 * (size_t)N));
+        LAUNCH(c, k_soa_to_aos_range, cdiv64(3 * N, 256), 256, g, c->vec[V_U], node0, N, tmp);
+        cudaError_t e = cudaMemcpyAsync(u_loc.data(), tmp, sizeof(double) * 3 * (size_t)N, cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        cudaFree(tmp);
+        if (e != cudaSuccess) FAIL(c, MACROC_ERR_CUDA, "write_pvtu: %s", cudaGetErrorString(e));
+    }
+    const int64_t nelem = c->ne_owned;
+    std::vector<double> eps((size_t)48 * std::max<int64_t>(nelem, 1)), sig((size_t)48 * std::max<int64_t>(nelem, 1));
+    if (c->cfg.material == MACROC_MAT_PER_GP) {
+        // strain from u (output.c:219-231), stress as the material model left it (output.c:245)
+        if ((rc = ensure_gp_arrays(c, false))) return rc;
+        if (nelem > 0) LAUNCH(c, k_strain_stress, cdiv64(nelem, 128), 128, g, s.ezs, s.nez, c->er.ne_ext, c->vec[V_U], c->strain, (double *)nullptr);
+    } else if ((rc = macroc_set_strains(c, 1)))
+        return rc;
+    if ((rc = gp_download(c, c->strain, eps.data(), 6))) return rc;
+    if ((rc = gp_download(c, c->stress, sig.data(), 6))) return rc;
+
+    snprintf(name, sizeof(name), "%s-subdo-%d.vtu", file_prefix, s.rank);
+    FILE *fp = fopen(name, "w");
+    if (!fp) FAIL(c, 65, "write_pvtu: cannot open %s", name);
+    fprintf(fp,
+            "<?xml version=\"1.0\"?>\n"
+            "<VTKFile type=\"UnstructuredGrid\" version=\"0.1\" byte_order=\"LittleEndian\">\n"
+            "<UnstructuredGrid>\n"
+            "<Piece NumberOfPoints=\"%d\" NumberOfCells=\"%d\">\n"
+            "<Points>\n", (int)N, (int)nelem);
+    fprintf(fp, "<DataArray type=\"Float64\" Name=\"Position\" NumberOfComponents=\"3\" format=\"ascii\">\n");
+    for (int k = s.Zs; k < s.Zs + s.Zm; ++k)
+        for (int j = 0; j < s.NY; ++j)
+            for (int i = 0; i < s.NX; ++i) fprintf(fp, "%01.6e\t%01.6e\t%01.6e\n", i * c->geo.dx, j * c->geo.dy, k * c->geo.dz);
+    fprintf(fp, "</DataArray>\n</Points>\n<Cells>\n");
+    fprintf(fp, "<DataArray type=\"Int32\" Name=\"connectivity\" NumberOfComponents=\"1\" format=\"ascii\">\n");
+    for (int ek = 0; ek < s.nez; ++ek)
+        for (int ej = 0; ej < s.ney; ++ej)
+            for (int ei = 0; ei < s.nex; ++ei) {
+                // DMDAGetElements: local ghosted ids, counter-clockwise bottom face then top face
+                const int64_t sx = 1, sy = s.NX, sz = g.npl;
+                const int64_t b0 = ei + sy * ej + sz * (int64_t)(s.ezs + ek - s.Zs);
+                const int64_t ids[8] = {b0, b0 + sx, b0 + sx + sy, b0 + sy, b0 + sz, b0 + sx + sz, b0 + sx + sy + sz, b0 + sy + sz};
+                for (int n = 0; n < 8; ++n) fprintf(fp, "%-6d\t", (int)ids[n]);
+                fprintf(fp, "\n");
+            }
+    fprintf(fp, "</DataArray>\n");
+    fprintf(fp, "<DataArray type=\"Int32\" Name=\"offsets\" NumberOfComponents=\"1\" format=\"ascii\">\n");
+    for (int64_t e = 1; e < nelem + 1; ++e) fprintf(fp, "%d\t", (int)(e * 8));
+    fprintf(fp, "\n</DataArray>\n");
+    fprintf(fp, "<DataArray type=\"UInt8\"  Name=\"types\" NumberOfComponents=\"1\" format=\"ascii\">\n");
+    for (int64_t e = 0; e < nelem; ++e) fprintf(fp, "12\t");
+    fprintf(fp, "\n</DataArray>\n</Cells>\n<PointData Vectors=\"displ\">\n");
+    fprintf(fp, "<DataArray type=\"Float64\" Name=\"displ\" NumberOfComponents=\"3\" format=\"ascii\" >\n");
+    for (int64_t n = 0; n < N; ++n) fprintf(fp, "%01.6e\t%01.6e\t%01.6e\n", u_loc[3 * n], u_loc[3 * n + 1], u_loc[3 * n + 2]);
+    fprintf(fp, "</DataArray>\n</PointData>\n<CellData>\n");
+    fprintf(fp, "<DataArray type=\"Int32\" Name=\"part\" NumberOfComponents=\"1\" format=\"ascii\">\n");
+    for (int64_t e = 0; e < nelem; ++e) fprintf(fp, "%d\t", s.rank);
+    fprintf(fp, "\n</DataArray>\n");
+    fprintf(fp, "<DataArray type=\"Float64\" Name=\"cost\" NumberOfComponents=\"1\" format=\"ascii\">\n");
+    for (int64_t e = 0; e < nelem; ++e) fprintf(fp, "%lf\t", 0.);
+    fprintf(fp, "\n</DataArray>\n");
+    fprintf(fp, "<DataArray type=\"Int32\" Name=\"non-linear\" NumberOfComponents=\"1\" format=\"ascii\">\n");
+    for (int64_t e = 0; e < nelem; ++e) fprintf(fp, "%d\t", 0);
+    fprintf(fp, "\n</DataArray>\n");
+    for (int pass = 0; pass < 2; ++pass) {
+        const std::vector<double> &v = pass == 0 ? eps : sig;
+        fprintf(fp, "<DataArray type=\"Float64\" Name=\"%s\" NumberOfComponents=\"6\" format=\"ascii\">", pass == 0 ? "strain" : "stress");
+        for (int64_t e = 0; e < nelem; ++e) {
+            double acc[6] = {0, 0, 0, 0, 0, 0};
+            for (int gp = 0; gp < 8; ++gp)
+                for (int i = 0; i < 6; ++i) acc[i] += v[(size_t)(e * 8 + gp) * 6 + i] * c->geo.wg;     // output.c:230,247
+            for (int i = 0; i < 6; ++i) fprintf(fp, "%e\t", acc[i]);
+        }
+        fprintf(fp, "\n</DataArray>\n");
+    }
+    fprintf(fp, "</CellData>\n</Piece>\n</UnstructuredGrid>\n</VTKFile>\n");
+    fclose(fp);
+    return MACROC_OK;
 }
 
 // ---------------------------------------------------------------------------

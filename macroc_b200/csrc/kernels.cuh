@@ -630,6 +630,16 @@ __global__ void k_soa_to_aos(GridDev g, const double *__restrict__ in, double *_
     out[e] = in[d * g.S + g.G + ln];
 }
 
+// owned + ghost planes -> interleaved host layout; node0 may be negative (lower ghost plane)
+__global__ void k_soa_to_aos_range(GridDev g, const double *__restrict__ in, int64_t node0, int64_t nnodes,
+                                   double *__restrict__ out)
+{
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= 3 * nnodes) return;
+    int64_t ln = node0 + e / 3; int d = (int)(e % 3);
+    out[e] = in[d * g.S + g.G + ln];
+}
+
 __global__ void k_export_blocks(GridDev g, const double *__restrict__ A, int64_t node0, int64_t nnodes,
                                 double *__restrict__ out /* [nnodes][243] */)
 {

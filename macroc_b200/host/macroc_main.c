@@ -120,6 +120,11 @@ int main(int argc, char **argv)
             printf("F_trial_max             : %e\n", 0.);
             fprintf(file_out, "%d\t%e\t%e\t%e\t%e\t%d\n", time_s, time_s * cfg.dt, U, force, 0., 0);   /* main.c:96 */
         }
+        if (cfg.vtu_freq > 0 && time_s % cfg.vtu_freq == 0) {     /* main.c:100-108 */
+            char file_prefix[4096];
+            snprintf(file_prefix, sizeof(file_prefix), "solution_%d", time_s);
+            CHK(macroc_write_pvtu(ctx, file_prefix));
+        }
     }
     CHK(macroc_device_synchronize(ctx));
     double t2 = wtime();

@@ -54,6 +54,15 @@ def main():
                                 ksp_its=np.array([k[1] for k in ksp]), newton_lines=np.array(newton),
                                 rowptr=rowptr, col=col, val=val, b=b, x=x, u=u, force=info[:, 3], U=info[:, 2])
             print(name, "res", res[:4], "ksp", ksp[:3])
+    # VTU output of the reference (src/output.c) for one case: -vtu_freq 1, keep the last step
+    import shutil
+    with tempfile.TemporaryDirectory() as d:
+        args = ["-da_grid_x", 5, "-da_grid_y", 3, "-da_grid_z", 4, "-ts", 3, "-bc_type", 0, "-vtu_freq", 1]
+        O.run_reference(args, d)
+        os.makedirs(os.path.join(out_dir, "vtu"), exist_ok=True)
+        for f in ("solution_2.pvtu", "solution_2-subdo-0.vtu"):
+            shutil.copy(os.path.join(d, f), os.path.join(out_dir, "vtu", "ctest_5x3x4_bending_" + f))
+        print("vtu fixtures written")
 
 
 if __name__ == "__main__":

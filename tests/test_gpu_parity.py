@@ -341,3 +341,32 @@ def test_gpu_material_model_writes_device_arrays_in_place():
     assert m.assembly_res() == pytest.approx(o.assembly_res(), rel=1e-12)
     o.assembly_jac(); m.assembly_jac()
     assert rel_err(m.get_matrix_blocks(), o.block_stencil()) < TOL_MAT
+
+
+def test_vtu_output_matches_reference_files(tmp_path, monkeypatch):
+    """write_pvtu (src/output.c): same files as the reference binary wrote for the same run
+    (tests/golden/vtu, produced by tests/golden/make_golden.py): identical text structure,
+    integers identical, floating-point tokens to solver tolerance."""
+    import os, re
+    from helpers import GOLDEN_DIR
+    cfg = M.Config.from_args("-da_grid_x 5 -da_grid_y 3 -da_grid_z 4 -ts 3 -bc_type 0 -vtu_freq 1".split())
+    assert cfg.NX == 5
+    m = M.MacroC(cfg)
+    for t in range(3):
+        m.time_step(t)
+    monkeypatch.chdir(tmp_path)
+    m.write_pvtu("solution_2")
+    num = re.compile(r"^[-+]?(\d+\.?\d*|\.\d+)([eE][-+]?\d+)?$")
+    for f in ("solution_2.pvtu", "solution_2-subdo-0.vtu"):
+        mine = open(tmp_path / f).read().split("\n")
+        ref = open(os.path.join(GOLDEN_DIR, "vtu", "ctest_5x3x4_bending_" + f)).read().split("\n")
+        assert len(mine) == len(ref), f
+        for a, b in zip(mine, ref):
+            ta, tb = a.split("\t"), b.split("\t")
+            assert len(ta) == len(tb), (a[:80], b[:80])
+            for x, y in zip(ta, tb):
+                xs, ys = x.strip(), y.strip()
+                if num.match(ys) and ("e" in ys or "." in ys):
+                    assert float(xs) == pytest.approx(float(ys), rel=2e-5, abs=1e-9), (a[:80], b[:80])
+                else:
+                    assert xs == ys, (a[:120], b[:120])
