@@ -52,9 +52,11 @@ def load_known_its(n):
         return KNOWN_CG_ITS.get(n)
 
 
-def workload(n_gpus: int, grid: int):
+def workload(n_gpus: int, grid: int, override=None):
     nx = ny = grid
     nz = grid * n_gpus
+    if override and all(override):
+        nx, ny, nz = override
     nd = 3 * nx * ny * nz
     nb = (3 * nx - 2) * (3 * ny - 2) * (3 * nz - 2)
     return nx, ny, nz, nd, nb
@@ -169,7 +171,7 @@ def run_reference_arm(args):
     if rank != 0:
         return 0
     threads = os.cpu_count() or 1
-    nx, ny, nz, nd, nb = workload(args.gpus, args.grid)
+    nx, ny, nz, nd, nb = workload(args.gpus, args.grid, (args.nx, args.ny, args.nz))
     its = args.cg_its or load_known_its(args.gpus) or 1000
     cpu = CpuSample(threads)
     for _ in range(args.warmup):
@@ -247,12 +249,13 @@ def run_gpu_arm(args):
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
-    nx, ny, nz, nd, nb = workload(world, args.grid)
+    nx, ny, nz, nd, nb = workload(world, args.grid, (args.nx, args.ny, args.nz))
+    custom = bool(args.nx and args.ny and args.nz)
     op = M.OP_MATRIX_FREE if args.matrix_free else M.OP_ASSEMBLED
     # the reference's default lengths (macroc.h:47-49), lz grows with the slab count so dz is fixed;
     # the element matrix is the unit-cube one scaled by wg, so CG counts do not
     # depend on the lengths -- they only keep |RES| above the absolute Newton tolerance 1e-1
-    cfg = M.Config(NX=nx, NY=ny, NZ=nz, pz=world, lx=50.0, ly=1.0, lz=50.0 * world, bc_type=M.BC_BENDING,
+    cfg = M.Config(NX=nx, NY=ny, NZ=nz, pz=world, lx=50.0, ly=1.0, lz=50.0 * (1 if custom else world), bc_type=M.BC_BENDING,
                    ts=args.steps + args.warmup + 1, device=local_rank, op=op)
     m = M.MacroC(cfg, rank=rank, nranks=world, unique_id=uid)
     nloc = m.local_ndof
@@ -384,7 +387,8 @@ def run_gpu_arm(args):
             known = {}
             if os.path.exists(KNOWN_CG_ITS_FILE):
                 known = json.load(open(KNOWN_CG_ITS_FILE))
-            known[str(world)] = int(round(its_step))
+            if not custom:
+                known[str(world)] = int(round(its_step))
             json.dump(known, open(KNOWN_CG_ITS_FILE, "w"))
         except Exception:
             pass
@@ -393,8 +397,10 @@ def run_gpu_arm(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": f"{nx}x{ny}x{nz} nodes hex8 cantilever (BASELINE configs[3]: 256^3 nodes per GPU, "
-                               "z-slab DMDA split; N=1 is configs[2]), bending BC, one Newton step per time step",
+        "config": {"workload": (f"{nx}x{ny}x{nz} nodes hex8 cantilever (custom grid, z-slab DMDA split), bending BC, one "
+                                "Newton step per time step") if custom else
+                               (f"{nx}x{ny}x{nz} nodes hex8 cantilever (BASELINE configs[3]: 256^3 nodes per GPU, "
+                                "z-slab DMDA split; N=1 is configs[2]), bending BC, one Newton step per time step"),
                    "grid": [nx, ny, nz], "ndof": nd, "operator": "matrix-free" if args.matrix_free else "assembled",
                    "parallelism": f"z-slabs x{world}", "ksp": "cg+jacobi rtol 1e-5", "l2": "inputs >> L2 (32 GB operator)",
                    "cg_iterations_per_step": its_step, "newton_its_per_step": newton,
@@ -428,6 +434,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--grid", type=int, default=256, help="nodes per direction per GPU")
+    ap.add_argument("--nx", type=int, default=0, help="custom global grid (with --ny --nz), e.g. 512 512 512 = BASELINE configs[4]")
+    ap.add_argument("--ny", type=int, default=0)
+    ap.add_argument("--nz", type=int, default=0)
     ap.add_argument("--matrix-free", action="store_true", help="solve with the matrix-free operator")
     ap.add_argument("--cg-its", type=int, default=0, help="(reference arm) CG iterations of one step")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
