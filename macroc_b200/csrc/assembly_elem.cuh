@@ -130,7 +130,7 @@ k_gather_forces(GridDev g, ElemRange er, int l0, int nl, int k0, int nk, const d
         r2 = (own & 4u) ? 0. : -r2;
         double *b0 = b + g.G + ln;
         b0[0] = r0; b0[g.S] = r1; b0[2 * g.S] = r2;
-        sq = r0 * r0 + r1 * r1 + r2 * r2;
+        if (owned_node(g, ln)) sq = r0 * r0 + r1 * r1 + r2 * r2;
     }
     double s = block_sum<8>(sq, sm);
     if (threadIdx.x == 0) partial[blockIdx.x] = s;

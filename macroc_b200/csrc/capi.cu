@@ -42,7 +42,9 @@ struct macroc_ctx {
     double2 *A = nullptr;
     bool A_valid = false, mf_ready = false;
     double *Ke = nullptr, *T = nullptr;
-    uint8_t *nodemask = nullptr;
+    uint8_t *nodemask = nullptr, *ghostflag = nullptr;
+    double *xy_halo = nullptr;       // 4 send + 4 receive staging buffers of the x / y halo
+    size_t xy_halo_stride = 0;
     double *consts = nullptr;        // device copy of {dsh[192], D[36], T[6561]} for bind_constants
     uint64_t id = 0;
     int64_t *bc_idx = nullptr;
@@ -193,7 +195,7 @@ extern "C" int macroc_partition(const macroc_config *cfg, int rank, int nranks, 
     Slab s;
     int rc = make_slab(*cfg, rank, nranks, &s);
     if (rc) return rc;
-    int32_t v[15] = {0, 0, s.zs, s.NX, s.NY, s.nzl, 0, 0, s.Zs, s.NX, s.NY, s.Zm, s.nex, s.ney, s.nez};
+    int32_t v[15] = {s.xs, s.ys, s.zs, s.xm, s.ym, s.nzl, s.Xs, s.Ys, s.Zs, s.Xm, s.Ym, s.Zm, s.nex, s.ney, s.nez};
     memcpy(out, v, sizeof(v));
     return MACROC_OK;
 }
@@ -263,7 +265,7 @@ static int ctx_free(macroc_ctx *c)
     for (int i = 0; i < V_COUNT; ++i) cudaFree(c->vec[i]);
     cudaFree(c->A); cudaFree(c->Ke); cudaFree(c->T); cudaFree(c->nodemask); cudaFree(c->bc_idx); cudaFree(c->bc_coef);
     cudaFree(c->partial); cudaFree(c->sums); cudaFree(c->sc); cudaFree(c->stage); cudaFree(c->strain); cudaFree(c->stress);
-    cudaFree(c->ctan); cudaFree(c->scratch); cudaFree(c->consts); cudaFree(c->gp_halo);
+    cudaFree(c->ctan); cudaFree(c->scratch); cudaFree(c->consts); cudaFree(c->gp_halo); cudaFree(c->ghostflag); cudaFree(c->xy_halo);
     if (c->device >= 0 && c->device < 64 && g_const_owner[c->device] == c->id) g_const_owner[c->device] = 0;
     cudaFree(c->flush);
     if (c->sums_host) cudaFreeHost(c->sums_host);
@@ -286,7 +288,9 @@ extern "C" int macroc_create(const macroc_config *cfg, int rank, int nranks, con
     *out = nullptr;
     Slab slab;
     int rc = make_slab(*cfg, rank, nranks, &slab);
-    if (rc) FAIL((macroc_ctx *)nullptr, rc, "macroc_create: unsupported decomposition (z-slabs only: px=py=1, pz=nranks<=NZ)");
+    if (rc) FAIL((macroc_ctx *)nullptr, rc, "macroc_create: -da_processors_x/y/z do not factor the rank count or exceed the grid");
+    if (slab.xy_split() && cfg->material == MACROC_MAT_PER_GP)
+        FAIL((macroc_ctx *)nullptr, MACROC_ERR_UNSUPPORTED, "macroc_create: per-Gauss-point material arrays need a z-slab decomposition (px = py = 1)");
     if (cfg->bc_type != MACROC_BC_BENDING && cfg->bc_type != MACROC_BC_CIRCLE)
         FAIL((macroc_ctx *)nullptr, MACROC_ERR_ARG, "macroc_create: bc_type must be 0 or 1");
     if (nranks > 1 && !id128) FAIL((macroc_ctx *)nullptr, MACROC_ERR_ARG, "macroc_create: nranks > 1 needs a unique id");
@@ -312,6 +316,8 @@ extern "C" int macroc_create(const macroc_config *cfg, int rank, int nranks, con
     GridDev &g = c->g;
     g.NX = slab.NX; g.NY = slab.NY; g.NZ = slab.NZ; g.zs = slab.zs; g.nzl = slab.nzl;
     g.npl = slab.npl; g.nloc = slab.nloc;
+    g.Xs = slab.Xs; g.Ys = slab.Ys; g.ox0 = slab.xs - slab.Xs; g.oy0 = slab.ys - slab.Ys; g.xm = slab.xm; g.ym = slab.ym;
+    g.ghost = nullptr;
     g.G = (int)(((slab.npl + slab.NX + 1 + 31) / 32) * 32);
     g.ntiles = (slab.nloc + TILE_NODES - 1) / TILE_NODES;
     g.S = g.ntiles * TILE_NODES + 2 * (int64_t)g.G + 32;
@@ -334,34 +340,36 @@ extern "C" int macroc_create(const macroc_config *cfg, int rank, int nranks, con
 
     // element bookkeeping: DMDA-owned layers plus, for the gather-form assembly, the first layer
     // of the upper neighbour (integrated redundantly / received as Gauss-point halo)
-    c->er.ezs = slab.ezs; c->er.nex = slab.nex; c->er.ney = slab.ney;
+    // (in x and y the kernels integrate every element of the local box; for z-slabs these are
+    // exactly the DMDA-owned ones)
+    c->er.ezs = slab.ezs; c->er.nex = slab.lnex; c->er.ney = slab.lney;
     c->er.nez_ext = slab.nez + (slab.has_upper() ? 1 : 0);
-    c->ne_owned = (int64_t)slab.nex * slab.ney * slab.nez;
-    c->ne_ext = (int64_t)slab.nex * slab.ney * c->er.nez_ext;
+    c->ne_owned = (int64_t)slab.lnex * slab.lney * slab.nez;
+    c->ne_ext = (int64_t)slab.lnex * slab.lney * c->er.nez_ext;
     c->er.ne_ext = std::max<int64_t>(c->ne_ext, 1);
     {
         // residual scratch: 24 doubles per element of a chunk of node planes (<= ~256 MB)
-        int64_t per_layer = std::max<int64_t>((int64_t)slab.nex * slab.ney, 1);
+        int64_t per_layer = std::max<int64_t>((int64_t)slab.lnex * slab.lney, 1);
         int64_t max_layers = std::max<int64_t>(2, ((int64_t)256 << 20) / (per_layer * 24 * 8));
         c->chunk_planes = (int)std::min<int64_t>(slab.nzl, max_layers - 1);
         if (c->chunk_planes < 1) c->chunk_planes = 1;
         CUC(cudaMalloc(&c->scratch, sizeof(double) * 24 * per_layer * (c->chunk_planes + 1)));
     }
-    // Dirichlet bookkeeping: the reference's lists (bc_init) -> per-node dof mask
-    // over the padded slab (ghost planes included) + owned (index, coef) pairs.
+    // Dirichlet bookkeeping: the reference's lists (bc_init over the ghosted box) -> per-node dof
+    // mask over the padded local array (ghost planes included) + (index, coef) pairs of the local
+    // nodes in the owned planes; x/y ghost flags for the reductions.
     {
-        std::vector<int32_t> ix; std::vector<double> cf;
-        build_bc_lists(*cfg, slab, ix, cf);
+        std::vector<BcEntry> ent;
+        int nbcs = 0;
+        build_bc_entries(*cfg, slab, ent, &nbcs);
         std::vector<uint8_t> mask((size_t)g.S, 0);
         std::vector<int64_t> own_idx; std::vector<double> own_coef;
-        const int64_t first = (int64_t)slab.zs * slab.npl, last = first + slab.nloc;
-        for (size_t q = 0; q < ix.size(); ++q) {
-            if (ix[q] < 0) continue;
-            int64_t node = ix[q] / 3; int d = ix[q] % 3;
-            int64_t pos = g.G + (node - first);              // may fall in a ghost plane
+        for (const BcEntry &e : ent) {
+            const int64_t ln = (e.i - slab.Xs) + (int64_t)slab.NX * (e.j - slab.Ys) + slab.npl * (int64_t)(e.k - slab.zs);
+            const int64_t pos = g.G + ln;
             if (pos < 0 || pos >= g.S) continue;
-            mask[(size_t)pos] |= (uint8_t)(1u << d);
-            if (node >= first && node < last) { own_idx.push_back(d * g.S + pos); own_coef.push_back(cf[q]); }
+            mask[(size_t)pos] |= (uint8_t)(1u << e.d);
+            if (e.k >= slab.zs && e.k < slab.zs + slab.nzl) { own_idx.push_back(e.d * g.S + pos); own_coef.push_back(e.coef); }
         }
         c->nbc = (int)own_idx.size();
         CUC(cudaMalloc(&c->nodemask, (size_t)g.S));
@@ -371,6 +379,20 @@ extern "C" int macroc_create(const macroc_config *cfg, int rank, int nranks, con
             CUC(cudaMalloc(&c->bc_coef, sizeof(double) * c->nbc));
             CUC(cudaMemcpyAsync(c->bc_idx, own_idx.data(), sizeof(int64_t) * c->nbc, cudaMemcpyHostToDevice, c->stream));
             CUC(cudaMemcpyAsync(c->bc_coef, own_coef.data(), sizeof(double) * c->nbc, cudaMemcpyHostToDevice, c->stream));
+        }
+        if (slab.xy_split()) {
+            std::vector<uint8_t> gh((size_t)g.S, 0);
+            for (int k = 0; k < slab.nzl; ++k)
+                for (int j = 0; j < slab.NY; ++j)
+                    for (int i = 0; i < slab.NX; ++i) {
+                        bool owned = i >= g.ox0 && i < g.ox0 + g.xm && j >= g.oy0 && j < g.oy0 + g.ym;
+                        gh[(size_t)(g.G + i + (int64_t)slab.NX * j + slab.npl * k)] = owned ? 0 : 1;
+                    }
+            CUC(cudaMalloc(&c->ghostflag, (size_t)g.S));
+            CUC(cudaMemcpyAsync(c->ghostflag, gh.data(), (size_t)g.S, cudaMemcpyHostToDevice, c->stream));
+            g.ghost = c->ghostflag;
+            c->xy_halo_stride = (size_t)3 * slab.nzl * std::max(slab.NX, slab.NY);
+            CUC(cudaMalloc(&c->xy_halo, sizeof(double) * 8 * c->xy_halo_stride));
         }
         CUC(cudaStreamSynchronize(c->stream));
     }
@@ -406,27 +428,65 @@ extern "C" int macroc_create(const macroc_config *cfg, int rank, int nranks, con
 // halo + reductions
 // ---------------------------------------------------------------------------
 
-// DMGlobalToLocal (assembly.c:40-41 and inside every MatMult): one node plane
-// per side and component over NCCL send/recv.
-static int halo_exchange(macroc_ctx *c, double *v, cudaStream_t st)
+// x / y phases of DMGlobalToLocal for a general DMDA box: the owned boundary column (row) of the
+// owned planes goes to the neighbour's ghost column (row).  Run x, then y (rows include the x
+// ghost columns just received), then z (planes include both): edge and corner ghosts arrive
+// without diagonal messages.
+static int halo_exchange_xy(macroc_ctx *c, double *v, cudaStream_t st)
+{
+    const GridDev &g = c->g;
+    const Slab &s = c->slab;
+    if (!c->comm || !s.xy_split()) return MACROC_OK;
+    for (int axis = 0; axis < 2; ++axis) {
+        const int lo = s.nb[2 * axis], hi = s.nb[2 * axis + 1];
+        if (lo < 0 && hi < 0) continue;
+        const int len = axis == 0 ? g.NY : g.NX, ext = axis == 0 ? g.NX : g.NY;
+        const int first_owned = axis == 0 ? g.ox0 : g.oy0, last_owned = first_owned + (axis == 0 ? g.xm : g.ym) - 1;
+        const size_t cnt = (size_t)3 * g.nzl * len;
+        double *sb_lo = c->xy_halo + (4 * axis + 0) * c->xy_halo_stride, *sb_hi = c->xy_halo + (4 * axis + 1) * c->xy_halo_stride;
+        double *rb_lo = c->xy_halo + (4 * axis + 2) * c->xy_halo_stride, *rb_hi = c->xy_halo + (4 * axis + 3) * c->xy_halo_stride;
+        const int blocks = cdiv64((int64_t)cnt, 256);
+        if (lo >= 0) { k_halo_pack_xy<<<blocks, 256, 0, st>>>(g, v, sb_lo, axis, first_owned, 1); c->launches++; }
+        if (hi >= 0) { k_halo_pack_xy<<<blocks, 256, 0, st>>>(g, v, sb_hi, axis, last_owned, 1); c->launches++; }
+        NC(c, ncclGroupStart());
+        if (lo >= 0) { NC(c, ncclSend(sb_lo, cnt, ncclDouble, lo, c->comm, st)); NC(c, ncclRecv(rb_lo, cnt, ncclDouble, lo, c->comm, st)); }
+        if (hi >= 0) { NC(c, ncclSend(sb_hi, cnt, ncclDouble, hi, c->comm, st)); NC(c, ncclRecv(rb_hi, cnt, ncclDouble, hi, c->comm, st)); }
+        NC(c, ncclGroupEnd());
+        if (lo >= 0) { k_halo_pack_xy<<<blocks, 256, 0, st>>>(g, v, rb_lo, axis, 0, 0); c->launches++; }
+        if (hi >= 0) { k_halo_pack_xy<<<blocks, 256, 0, st>>>(g, v, rb_hi, axis, ext - 1, 0); c->launches++; }
+    }
+    return MACROC_OK;
+}
+
+// DMGlobalToLocal (assembly.c:40-41 and inside every MatMult), z phase: one node plane per side
+// and component over NCCL send/recv.
+static int halo_exchange_z(macroc_ctx *c, double *v, cudaStream_t st)
 {
     if (!c->comm) return MACROC_OK;
     const GridDev &g = c->g;
     const Slab &s = c->slab;
+    if (!s.has_lower() && !s.has_upper()) return MACROC_OK;
     NC(c, ncclGroupStart());
     for (int d = 0; d < 3; ++d) {
         double *base = v + d * g.S + g.G;
         if (s.has_lower()) {
-            NC(c, ncclSend(base, (size_t)g.npl, ncclDouble, s.rank - 1, c->comm, st));
-            NC(c, ncclRecv(base - g.npl, (size_t)g.npl, ncclDouble, s.rank - 1, c->comm, st));
+            NC(c, ncclSend(base, (size_t)g.npl, ncclDouble, s.nb[4], c->comm, st));
+            NC(c, ncclRecv(base - g.npl, (size_t)g.npl, ncclDouble, s.nb[4], c->comm, st));
         }
         if (s.has_upper()) {
-            NC(c, ncclSend(base + g.nloc - g.npl, (size_t)g.npl, ncclDouble, s.rank + 1, c->comm, st));
-            NC(c, ncclRecv(base + g.nloc, (size_t)g.npl, ncclDouble, s.rank + 1, c->comm, st));
+            NC(c, ncclSend(base + g.nloc - g.npl, (size_t)g.npl, ncclDouble, s.nb[5], c->comm, st));
+            NC(c, ncclRecv(base + g.nloc, (size_t)g.npl, ncclDouble, s.nb[5], c->comm, st));
         }
     }
     NC(c, ncclGroupEnd());
     return MACROC_OK;
+}
+
+static int halo_exchange(macroc_ctx *c, double *v, cudaStream_t st)
+{
+    int rc = halo_exchange_xy(c, v, st);
+    if (rc) return rc;
+    return halo_exchange_z(c, v, st);
 }
 
 static int allreduce_sums(macroc_ctx *c, int n)
@@ -480,14 +540,14 @@ static int halo_gp_layer(macroc_ctx *c, double *arr, int nq)
 {
     if (!c->comm) return MACROC_OK;
     const Slab &s = c->slab;
-    const int64_t per_layer = (int64_t)s.nex * s.ney;
+    const int64_t per_layer = (int64_t)s.lnex * s.lney;
     const size_t cnt = (size_t)per_layer * nq;
     if (!c->gp_halo) CU(c, cudaMalloc(&c->gp_halo, sizeof(double) * 2 * (size_t)per_layer * 288));
     double *sbuf = c->gp_halo, *rbuf = c->gp_halo + (size_t)per_layer * 288;
     if (s.has_lower()) LAUNCH(c, k_gp_layer_copy, cdiv64(cnt, 256), 256, nq, per_layer, c->er.ne_ext, (int64_t)0, arr, sbuf, 1);
     NC(c, ncclGroupStart());
-    if (s.has_lower()) NC(c, ncclSend(sbuf, cnt, ncclDouble, s.rank - 1, c->comm, c->stream));
-    if (s.has_upper()) NC(c, ncclRecv(rbuf, cnt, ncclDouble, s.rank + 1, c->comm, c->stream));
+    if (s.has_lower()) NC(c, ncclSend(sbuf, cnt, ncclDouble, s.nb[4], c->comm, c->stream));
+    if (s.has_upper()) NC(c, ncclRecv(rbuf, cnt, ncclDouble, s.nb[5], c->comm, c->stream));
     NC(c, ncclGroupEnd());
     if (s.has_upper()) LAUNCH(c, k_gp_layer_copy, cdiv64(cnt, 256), 256, nq, per_layer, c->er.ne_ext, c->ne_owned, arr, rbuf, 0);
     return MACROC_OK;
@@ -502,6 +562,7 @@ extern "C" int macroc_set_strains(macroc_ctx *c, int materialize)
     if (rc) return rc;
     if (materialize || c->cfg.material == MACROC_MAT_PER_GP) {
         const Slab &s = c->slab;
+        if (s.xy_split()) FAIL(c, MACROC_ERR_UNSUPPORTED, "Gauss-point arrays need a z-slab decomposition (px = py = 1)");
         if ((rc = ensure_gp_arrays(c, false))) return rc;
         // strain of the owned elements; stress = D strain as a by-product for the uniform law
         if (c->ne_owned > 0)
@@ -600,7 +661,7 @@ static int residual_launch(macroc_ctx *c, int *nparts_out)
         const int lay_lo = std::max(s.zs + k0 - 1, c->er.ezs), lay_hi = std::min(s.zs + k0 + nk - 1, last_stored);
         const int l0 = lay_lo - c->er.ezs, nl = lay_hi - lay_lo + 1;
         if (nl > 0) {
-            int64_t n = (int64_t)s.nex * s.ney * nl;
+            int64_t n = (int64_t)s.lnex * s.lney * nl;
             if (per_gp) LAUNCH(c, k_elem_forces<true>, cdiv64(n, 128), 128, g, c->er, l0, nl, c->geo.wg, c->vec[V_U], c->stress, c->scratch);
             else LAUNCH(c, k_elem_forces<false>, cdiv64(n, 128), 128, g, c->er, l0, nl, c->geo.wg, c->vec[V_U], c->stress, c->scratch);
         }
@@ -732,14 +793,17 @@ static int apply_operator(macroc_ctx *c, int op, double *p, double *w, bool with
     }
     const bool split = comm && lo_end > 0;
     if (comm) {
-        CU(c, cudaEventRecord(c->ev_ready, c->stream));
+        // x / y ghost columns are needed by every tile: exchange them first, in stream order
+        int rc = halo_exchange_xy(c, p, c->stream);
+        if (rc) return rc;
         if (split) {
+            CU(c, cudaEventRecord(c->ev_ready, c->stream));
             CU(c, cudaStreamWaitEvent(c->comm_stream, c->ev_ready, 0));
-            int rc = halo_exchange(c, p, c->comm_stream);
+            rc = halo_exchange_z(c, p, c->comm_stream);
             if (rc) return rc;
             CU(c, cudaEventRecord(c->ev_halo, c->comm_stream));
         } else {
-            int rc = halo_exchange(c, p, c->stream);
+            rc = halo_exchange_z(c, p, c->stream);
             if (rc) return rc;
         }
     }
@@ -934,11 +998,15 @@ extern "C" int macroc_calc_force(macroc_ctx *c, double *force)
     CU(c, cudaSetDevice(c->device));
     { int _rc = bind_constants(c); if (_rc) return _rc; }
     const Slab &s = c->slab;
-    int64_t count = c->cfg.bc_type == MACROC_BC_BENDING ? (int64_t)s.ney * s.nez : (int64_t)s.nex * s.nez;
+    { int _rc = halo_exchange(c, c->vec[V_U], c->stream); if (_rc) return _rc; }   // ghost nodes of u may be stale after update_u
+    // forces.c:75 (bending: ranks that own the X = LX face) / :133 (circle: ghost start + owned
+    // count, the reference's mix) decide which ranks contribute
+    const bool on_face = c->cfg.bc_type == MACROC_BC_BENDING ? (s.xs + s.xm == s.gNX) : (s.Ys + s.ym == s.gNY);
+    int64_t count = !on_face ? 0 : (c->cfg.bc_type == MACROC_BC_BENDING ? (int64_t)s.ney * s.nez : (int64_t)s.nex * s.nez);
     double local = 0.;
     if (count > 0) {
         int nblk = cdiv64(count, 128);
-        LAUNCH(c, k_force, nblk, 128, c->g, s.ezs, s.nez, c->cfg.bc_type, c->geo.dx, c->geo.dy, c->geo.dz, c->cfg.lx,
+        LAUNCH(c, k_force, nblk, 128, c->g, s.ezs, s.nez, s.exs - s.Xs, s.eys - s.Ys, s.nex, s.ney, c->cfg.bc_type, c->geo.dx, c->geo.dy, c->geo.dz, c->cfg.lx,
                c->cfg.lz, c->geo.rad, c->vec[V_U],
                (c->cfg.material == MACROC_MAT_PER_GP && c->stress) ? c->stress : (const double *)nullptr, c->er.ne_ext,
                c->partial);
@@ -989,8 +1057,8 @@ extern "C" int macroc_time_step(macroc_ctx *c, int time_s, int *newton_its, doub
 // boundary copies
 // ---------------------------------------------------------------------------
 
-extern "C" int64_t macroc_local_ndof(const macroc_ctx *c) { return c ? 3 * c->g.nloc : 0; }
-extern "C" int64_t macroc_global_ndof(const macroc_ctx *c) { return c ? 3 * (int64_t)c->g.NX * c->g.NY * c->g.NZ : 0; }
+extern "C" int64_t macroc_local_ndof(const macroc_ctx *c) { return c ? 3 * (int64_t)c->g.xm * c->g.ym * c->g.nzl : 0; }
+extern "C" int64_t macroc_global_ndof(const macroc_ctx *c) { return c ? 3 * (int64_t)c->slab.gNX * c->slab.gNY * c->slab.gNZ : 0; }
 
 static double *which_vec(macroc_ctx *c, int which)
 {
@@ -1008,7 +1076,7 @@ extern "C" int macroc_set_vec(macroc_ctx *c, int which, const double *host)
     double *v = which_vec(c, which);
     if (!v) FAIL(c, MACROC_ERR_ARG, "set_vec: unknown vector %d", which);
     CU(c, cudaSetDevice(c->device));
-    int64_t n = 3 * c->g.nloc;
+    int64_t n = macroc_local_ndof(c);
     CU(c, cudaMemcpyAsync(c->stage, host, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
     LAUNCH(c, k_aos_to_soa, cdiv64(n, 256), 256, c->g, c->stage, v);
     CU(c, cudaStreamSynchronize(c->stream));
@@ -1021,7 +1089,7 @@ extern "C" int macroc_get_vec(macroc_ctx *c, int which, double *host)
     double *v = which_vec(c, which);
     if (!v) FAIL(c, MACROC_ERR_ARG, "get_vec: unknown vector %d", which);
     CU(c, cudaSetDevice(c->device));
-    int64_t n = 3 * c->g.nloc;
+    int64_t n = macroc_local_ndof(c);
     LAUNCH(c, k_soa_to_aos, cdiv64(n, 256), 256, c->g, v, c->stage);
     CU(c, cudaMemcpyAsync(host, c->stage, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
@@ -1036,8 +1104,9 @@ extern "C" int macroc_get_matrix_blocks(macroc_ctx *c, double *host)
     const int64_t chunk = 1 << 16;                 // nodes per export chunk
     double *tmp = nullptr;
     CU(c, cudaMalloc(&tmp, sizeof(double) * 243 * chunk));
-    for (int64_t n0 = 0; n0 < c->g.nloc; n0 += chunk) {
-        int64_t nn = std::min<int64_t>(chunk, c->g.nloc - n0);
+    const int64_t nown = (int64_t)c->g.xm * c->g.ym * c->g.nzl;
+    for (int64_t n0 = 0; n0 < nown; n0 += chunk) {
+        int64_t nn = std::min<int64_t>(chunk, nown - n0);
         LAUNCH(c, k_export_blocks, cdiv64(nn * 243, 256), 256, c->g, reinterpret_cast<const double *>(c->A), n0, nn, tmp);
         cudaError_t e = cudaMemcpyAsync(host + n0 * 243, tmp, sizeof(double) * 243 * nn, cudaMemcpyDeviceToHost, c->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
@@ -1053,7 +1122,7 @@ extern "C" int macroc_matmult(macroc_ctx *c, int op, const double *x_host, doubl
     CU(c, cudaSetDevice(c->device));
     { int _rc = bind_constants(c); if (_rc) return _rc; }
     if (op == MACROC_OP_ASSEMBLED && !c->A_valid) FAIL(c, MACROC_ERR_ARG, "matmult: no assembled operator");
-    int64_t n = 3 * c->g.nloc;
+    int64_t n = macroc_local_ndof(c);
     CU(c, cudaMemcpyAsync(c->stage, x_host, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
     LAUNCH(c, k_aos_to_soa, cdiv64(n, 256), 256, c->g, c->stage, c->vec[V_P]);
     int rc = apply_operator(c, op, c->vec[V_P], c->vec[V_W], false, nullptr);
@@ -1085,6 +1154,7 @@ extern "C" int macroc_write_pvtu(macroc_ctx *c, const char *file_prefix)
     { int _rc = bind_constants(c); if (_rc) return _rc; }
     const Slab &s = c->slab;
     const GridDev &g = c->g;
+    if (s.xy_split()) FAIL(c, MACROC_ERR_UNSUPPORTED, "write_pvtu needs a z-slab decomposition (px = py = 1)");
     char name[4096];
     if (s.rank == 0) {
         snprintf(name, sizeof(name), "%s.pvtu", file_prefix);

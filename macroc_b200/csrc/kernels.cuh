@@ -35,13 +35,23 @@ __constant__ double c_D[36];                 // homogenised tangent (row-major 6
 __constant__ double c_T[27 * 243];
 
 struct GridDev {
-    int NX, NY, NZ;          // global grid
+    int NX, NY, NZ;          // LOCAL box extents in x and y (ghost columns/rows of x/y neighbours
+                             // included; = the global grid for z-slabs) and the global NZ
     int zs, nzl;             // owned planes
-    int64_t npl, nloc;       // nodes per plane / owned nodes
+    int64_t npl, nloc;       // local nodes per plane / local nodes of the owned planes
     int64_t S;               // SoA component stride (doubles)
-    int G;                   // padding (nodes) in front of owned node 0
+    int G;                   // padding (nodes) in front of local node 0
     int64_t ntiles;
+    int Xs, Ys;              // global coordinates of local node (0, 0)
+    int ox0, oy0, xm, ym;    // owned sub-box of the local box (DMDAGetCorners, local coordinates)
+    const uint8_t *ghost;    // 1 for local nodes owned by an x/y neighbour (excluded from reductions);
+                             // nullptr for z-slabs
 };
+
+__device__ __forceinline__ bool owned_node(const GridDev &g, int64_t ln)
+{
+    return g.ghost == nullptr || g.ghost[g.G + ln] == 0;
+}
 
 struct CgScalars {
     double beta, betaold, pw, zz, zr, dp, dp0, ttol, rtol, abstol, dtol;
@@ -268,7 +278,7 @@ k_spmv(GridDev g, const double2 *__restrict__ A, const double *__restrict__ p, d
         if (ln < g.nloc) {
             double *w0 = w + g.G + ln;
             w0[0] = a0; w0[g.S] = a1; w0[2 * g.S] = a2;
-            dot += a0 * pc0 + a1 * pc1 + a2 * pc2;
+            if (DOT && owned_node(g, ln)) dot += a0 * pc0 + a1 * pc1 + a2 * pc2;
         }
     }
     if (DOT) {
@@ -418,7 +428,7 @@ k_apply_mf3d(GridDev g, const uint8_t *__restrict__ nodemask, const double *__re
                 }
                 double *y0 = y + g.G + ln;
                 y0[0] = a0; y0[g.S] = a1; y0[2 * g.S] = a2;
-                dot += a0 * xc0 + a1 * xc1 + a2 * xc2;
+                if (DOT && owned_node(g, ln)) dot += a0 * xc0 + a1 * xc1 + a2 * xc2;
             }
         }
     }
@@ -550,24 +560,26 @@ __global__ void k_gp_layer_copy(int nq, int64_t per_layer, int64_t ne_ext, int64
 // forces.c:58-106 / :115-166: sum of the 8 Gauss-point stresses of the elements
 // next to the loaded boundary, component [3]*dy*dz (bending) or [1]*dx*dz (circle).
 __global__ void __launch_bounds__(128)
-k_force(GridDev g, int ezs, int nez, int bc_type, double dx, double dy, double dz, double lx, double lz,
-        double rad, const double *__restrict__ u, const double *__restrict__ stress_gp, int64_t ne_ext,
-        double *__restrict__ partial)
+k_force(GridDev g, int ezs, int nez, int lex0, int ley0, int onex, int oney, int bc_type, double dx, double dy,
+        double dz, double lx, double lz, double rad, const double *__restrict__ u,
+        const double *__restrict__ stress_gp, int64_t ne_ext, double *__restrict__ partial)
 {
+    // (lex0, ley0): first DMDA-owned element of the rank in local-box coordinates; onex x oney
+    // owned elements per layer (forces.c:69,126); nex, ney below are the local box's elements
     __shared__ double sm[4];
     int64_t nex = g.NX - 1, ney = g.NY - 1;
     int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     double f = 0.;
-    int64_t count = bc_type == 0 ? ney * nez : nex * nez;
+    int64_t count = bc_type == 0 ? (int64_t)oney * nez : (int64_t)onex * nez;
     if (t < count) {
         int ei, ej, ek;
         bool take = true;
-        if (bc_type == 0) { ei = (int)nex - 1; ej = (int)(t % ney); ek = (int)(t / ney) + ezs; }
+        if (bc_type == 0) { ei = lex0 + onex - 1; ej = ley0 + (int)(t % oney); ek = (int)(t / oney) + ezs; }
         else {
-            ei = (int)(t % nex); ej = (int)ney - 1; ek = (int)(t / nex) + ezs;
+            ei = lex0 + (int)(t % onex); ej = ley0 + oney - 1; ek = (int)(t / onex) + ezs;
             // forces.c:138-141: ghost start + local element index
             int sk = ezs;
-            double xx = __dsub_rn(lx / 2., __dadd_rn(__dmul_rn((double)ei, dx), dx / 2.));
+            double xx = __dsub_rn(lx / 2., __dadd_rn(__dmul_rn((double)(g.Xs + ei), dx), dx / 2.));
             double zz = __dsub_rn(lz / 2., __dadd_rn(__dmul_rn((double)(sk + (ek - ezs)), dz), dz / 2.));
             take = (__dadd_rn(__dmul_rn(xx, xx), __dmul_rn(zz, zz))) < rad * rad;
         }
@@ -614,19 +626,27 @@ __global__ void k_axpy1(GridDev g, double *__restrict__ y, const double *__restr
     y[q] += 1. * x[q];                              // VecAXPY(u, 1., du) main.c:79
 }
 
+// boundary layout (owned box, x fastest, dof-interleaved = the rank's part of the DMDA global
+// vector) <-> local SoA arrays
+__device__ __forceinline__ int64_t owned_to_local(const GridDev &g, int64_t on)
+{
+    const int64_t i = on % g.xm, j = (on / g.xm) % g.ym, k = on / ((int64_t)g.xm * g.ym);
+    return (g.ox0 + i) + (int64_t)g.NX * (g.oy0 + j) + g.npl * k;
+}
+
 __global__ void k_aos_to_soa(GridDev g, const double *__restrict__ in, double *__restrict__ out)
 {
     int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= 3 * g.nloc) return;
-    int64_t ln = e / 3; int d = (int)(e % 3);
+    if (e >= 3 * (int64_t)g.xm * g.ym * g.nzl) return;
+    int64_t ln = owned_to_local(g, e / 3); int d = (int)(e % 3);
     out[d * g.S + g.G + ln] = in[e];
 }
 
 __global__ void k_soa_to_aos(GridDev g, const double *__restrict__ in, double *__restrict__ out)
 {
     int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= 3 * g.nloc) return;
-    int64_t ln = e / 3; int d = (int)(e % 3);
+    if (e >= 3 * (int64_t)g.xm * g.ym * g.nzl) return;
+    int64_t ln = owned_to_local(g, e / 3); int d = (int)(e % 3);
     out[e] = in[d * g.S + g.G + ln];
 }
 
@@ -645,9 +665,23 @@ __global__ void k_export_blocks(GridDev g, const double *__restrict__ A, int64_t
 {
     int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= nnodes * 243) return;
-    int64_t ln = node0 + e / 243; int kk = (int)(e % 243);
+    int64_t ln = owned_to_local(g, node0 + e / 243); int kk = (int)(e % 243);   // node0, nnodes: owned-box order
     int64_t tile = ln / TILE_NODES; int lane = (int)(ln % TILE_NODES);
     out[e] = A[tile * TILE_DOUBLES + ((int64_t)(kk >> 1) * TILE_NODES + lane) * 2 + (kk & 1)];
+}
+
+// x / y halo of the general DMDA box: one column (x) or row (y) of the owned planes, all three
+// components, to / from a contiguous buffer.  axis 0: buf[(c*nzl + k)*NY + j] <-> v(idx, j, k);
+// axis 1: buf[(c*nzl + k)*NX + i] <-> v(i, idx, k).
+__global__ void k_halo_pack_xy(GridDev g, double *__restrict__ v, double *__restrict__ buf, int axis, int idx, int pack)
+{
+    const int64_t len = axis == 0 ? g.NY : g.NX, n = 3 * (int64_t)g.nzl * len;
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const int64_t a = t % len, k = (t / len) % g.nzl, c = t / (len * g.nzl);
+    const int64_t ln = axis == 0 ? idx + g.NX * a + g.npl * k : a + (int64_t)g.NX * idx + g.npl * k;
+    if (pack) buf[t] = v[c * g.S + g.G + ln];
+    else v[c * g.S + g.G + ln] = buf[t];
 }
 
 // fixed-order reduction of per-block partials: out[0..nout) = sum over blocks
@@ -674,7 +708,7 @@ __global__ void k_fill_pattern(GridDev g, const uint8_t *__restrict__ nodemask, 
     unsigned own = nodemask[g.G + ln];
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
-        double gd = (double)((ln + (int64_t)g.zs * g.npl) * 3 + d);
+        double gd = (double)((ln + (int64_t)g.zs * g.npl) * 3 + d) + 1e3 * g.Xs + 1e5 * g.Ys;
         v[d * g.S + g.G + ln] = ((own >> d) & 1u) ? 0. : sin(0.37 * gd) + 0.1;
     }
 }
@@ -708,8 +742,13 @@ k_cg_init(GridDev g, const double *__restrict__ b, const double *__restrict__ di
                 *reinterpret_cast<double2 *>(x + q) = make_double2(0., 0.);
                 *reinterpret_cast<double2 *>(r + q) = rv;
             } else { x[q] = 0.; r[q] = rv.x; }
-            zz = fma(z0, z0, zz); zr = fma(z0, rv.x, zr);
-            zz = fma(z1, z1, zz); zr = fma(z1, rv.y, zr);
+            if (g.ghost) {       // x/y ghost rows do not count
+                if (g.ghost[g.G + 2 * pr] == 0) { zz = fma(z0, z0, zz); zr = fma(z0, rv.x, zr); }
+                if (two && g.ghost[g.G + 2 * pr + 1] == 0) { zz = fma(z1, z1, zz); zr = fma(z1, rv.y, zr); }
+            } else {
+                zz = fma(z0, z0, zz); zr = fma(z0, rv.x, zr);
+                zz = fma(z1, z1, zz); zr = fma(z1, rv.y, zr);
+            }
         }
     }
     double s0 = block_sum<8>(zz, sm), s1 = block_sum<8>(zr, sm);
@@ -782,8 +821,13 @@ k_cg_update_xr(GridDev g, const CgScalars *__restrict__ s, const double *__restr
                 *reinterpret_cast<double2 *>(r + q) = rv;
             } else { x[q] = xv.x; r[q] = rv.x; rv.y = 0.; }
             const double z0 = rv.x * dv.x, z1 = two ? rv.y * dv.y : 0.;
-            zz = fma(z0, z0, zz); zr = fma(z0, rv.x, zr);
-            zz = fma(z1, z1, zz); zr = fma(z1, rv.y, zr);
+            if (g.ghost) {
+                if (g.ghost[g.G + 2 * pr] == 0) { zz = fma(z0, z0, zz); zr = fma(z0, rv.x, zr); }
+                if (two && g.ghost[g.G + 2 * pr + 1] == 0) { zz = fma(z1, z1, zz); zr = fma(z1, rv.y, zr); }
+            } else {
+                zz = fma(z0, z0, zz); zr = fma(z0, rv.x, zr);
+                zz = fma(z1, z1, zz); zr = fma(z1, rv.y, zr);
+            }
         }
     }
     double s0 = block_sum<8>(zz, sm), s1 = block_sum<8>(zr, sm);

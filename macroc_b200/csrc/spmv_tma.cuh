@@ -161,7 +161,7 @@ k_spmv_tma(GridDev g, const double2 *__restrict__ A, const double *__restrict__ 
         if (ln < g.nloc) {
             double *w0 = w + g.G + ln;
             w0[0] = a0; w0[g.S] = a1; w0[2 * g.S] = a2;
-            dot += a0 * pc0 + a1 * pc1 + a2 * pc2;
+            if (DOT && owned_node(g, ln)) dot += a0 * pc0 + a1 * pc1 + a2 * pc2;
         }
     }
     if (DOT) {

@@ -167,11 +167,28 @@ void orc_elem_res(const double *stress, double wg, double *be)
 /* PETSc's "squarish" PETSC_DECIDE factorisation of the communicator size for a
  * 3-D DMDA (restated from memory of DMSetUp_DA_3D; UNVERIFIED against a PETSc
  * build -- the z-slab configurations set px,py,pz explicitly). */
+static int squarish2(double A, double B, int fixed, int size, int *a, int *b)
+{
+    int aa = (int)(0.5 + sqrt(A * (double)size / (B * (double)fixed))), bb = 0;
+    if (!aa) aa = 1;
+    while (aa > 0) { bb = size / (aa * fixed); if (aa * bb * fixed == size) break; aa--; }
+    if (!aa) return 0;
+    if (A > B && aa < bb) { int t = aa; aa = bb; bb = t; }
+    *a = aa; *b = bb;
+    return 1;
+}
+
 static void decide_proc_grid(int M, int N, int P, int size, int *m_, int *n_, int *p_)
 {
-    int m = *m_, n = *n_, p = *p_;
-    if (m > 0 && n > 0 && p > 0) return;
-    if (m <= 0 && n <= 0 && p <= 0) {
+    int m = *m_ > 0 ? *m_ : 0, n = *n_ > 0 ? *n_ : 0, p = *p_ > 0 ? *p_ : 0;
+    if (m && n && p) return;
+    if (!m && n && p) m = size / (n * p);
+    else if (m && !n && p) n = size / (m * p);
+    else if (m && n && !p) p = size / (m * n);
+    else if (!m && !n && p) squarish2(M, N, p, size, &m, &n);
+    else if (!m && n && !p) squarish2(M, P, n, size, &m, &p);
+    else if (m && !n && !p) squarish2(N, P, m, size, &n, &p);
+    else {
         int pm;
         n = (int)(0.5 + pow(((double)N * N) * ((double)size) / ((double)P * M), 1. / 3.));
         if (!n) n = 1;
@@ -181,13 +198,6 @@ static void decide_proc_grid(int M, int N, int P, int size, int *m_, int *n_, in
         if (!m) m = 1;
         while (m > 0) { p = size / (m * n); if (m * n * p == size) break; m--; }
         if (M > P && m < p) { int t = m; m = p; p = t; }
-    } else {
-        /* partially specified: fill the unspecified ones greedily */
-        int known = (m > 0 ? m : 1) * (n > 0 ? n : 1) * (p > 0 ? p : 1);
-        int rest = size / known;
-        if (p <= 0) { p = rest; rest = 1; }
-        if (n <= 0) { n = rest; rest = 1; }
-        if (m <= 0) { m = rest; rest = 1; }
     }
     *m_ = m; *n_ = n; *p_ = p;
 }

@@ -34,7 +34,7 @@ def host_mode(args):
         if world > NZ:
             continue
         for bc in (M.BC_BENDING, M.BC_CIRCLE):
-            cfg = M.Config(NX=NX, NY=NY, NZ=NZ, bc_type=bc, lx=5.0, lz=6.0)
+            cfg = M.Config(NX=NX, NY=NY, NZ=NZ, bc_type=bc, lx=5.0, lz=6.0, px=1, py=1, pz=world)
             part = M.partition(cfg, rank, world)
             idx, coef = M.bc_lists(cfg, rank, world)
             parts = gather_objects(part)
@@ -62,7 +62,7 @@ def host_mode(args):
                 for i, c in zip(ix, cf):
                     if i >= 0:
                         assert merged.setdefault(int(i), float(c)) == float(c)
-            ix1, cf1 = M.bc_lists(cfg, 0, 1)
+            ix1, cf1 = M.bc_lists(M.Config(NX=NX, NY=NY, NZ=NZ, bc_type=bc, lx=5.0, lz=6.0), 0, 1)
             single = {int(i): float(c) for i, c in zip(ix1, cf1) if i >= 0}
             assert merged == single, (NX, NY, NZ, bc)
     # bench.py's max/sum-over-ranks helpers on the gloo backend
@@ -79,40 +79,57 @@ def gpu_mode(args):
     rank, world = dist.get_rank(), dist.get_world_size()
     local = int(os.environ.get("LOCAL_RANK", rank))
     torch.cuda.set_device(local)
-    cases = [(8, 5, 2 * world + 1, M.BC_BENDING, {}), (40, 3, 40, M.BC_CIRCLE, {}),
-             (33, 9, 4 * world + 3, M.BC_BENDING, dict(lx=10., ly=1., lz=1.)),
-             (9, 3, max(9, world), M.BC_CIRCLE, dict(lx=4., lz=4.))]
-    for (NX, NY, NZ, bc, extra) in cases:
+    zs = (1, 1, world)
+    cases = [(8, 5, 2 * world + 1, M.BC_BENDING, {}, zs), (40, 3, 40, M.BC_CIRCLE, {}, zs),
+             (33, 9, 4 * world + 3, M.BC_BENDING, dict(lx=10., ly=1., lz=1.), zs),
+             (9, 3, max(9, world), M.BC_CIRCLE, dict(lx=4., lz=4.), zs),
+             (8, 5, world, M.BC_BENDING, {}, zs),                       # one plane per rank
+             # general DMDA boxes: x split, y split, PETSC_DECIDE
+             (2 * world + 3, 6, 5, M.BC_BENDING, {}, (world, 1, 1)),
+             (9, 2 * world + 2, 7, M.BC_CIRCLE, dict(lx=4., lz=4.), (1, world, 1)),
+             (37, 11, 9, M.BC_BENDING, dict(lx=10., ly=1., lz=1.), (0, 0, 0))]
+    if world == 4:
+        cases += [(12, 10, 9, M.BC_BENDING, {}, (2, 2, 1)), (11, 5, 10, M.BC_CIRCLE, dict(lx=4., lz=4.), (2, 1, 2))]
+    if world == 8:
+        cases += [(12, 10, 9, M.BC_BENDING, {}, (2, 2, 2))]
+    for (NX, NY, NZ, bc, extra, pg) in cases:
         for op, material in ((M.OP_ASSEMBLED, M.MAT_UNIFORM), (M.OP_MATRIX_FREE, M.MAT_UNIFORM),
                              (M.OP_ASSEMBLED, M.MAT_PER_GP)):
+            if material == M.MAT_PER_GP and pg != zs:
+                continue                                     # Gauss-point arrays: z-slabs only
             box = [M.get_unique_id() if rank == 0 else None]
             dist.broadcast_object_list(box, src=0)
             ts = 3
-            cfg = M.Config(NX=NX, NY=NY, NZ=NZ, bc_type=bc, pz=world, ts=ts, ksp_rtol=1e-12, op=op, device=local,
-                           material=material, **extra)
+            cfg = M.Config(NX=NX, NY=NY, NZ=NZ, bc_type=bc, px=pg[0], py=pg[1], pz=pg[2], ts=ts, ksp_rtol=1e-12,
+                           op=op, device=local, material=material, **extra)
             m = M.MacroC(cfg, rank=rank, nranks=world, unique_id=box[0])
             logs = [m.time_step(t) for t in range(ts)]
             u_loc = m.get_vec(M.VEC_U)
             force = m.calc_force()
             x = np.sin(0.37 * np.arange(3 * NX * NY * NZ)) + 0.1
             p = M.partition(cfg, rank, world)
-            zs, zm = p["corners"][2], p["corners"][5]
-            sl = slice(3 * NX * NY * zs, 3 * NX * NY * (zs + zm))
+            xs0, ys0, zs0, xm, ym, zm = p["corners"]
+            box = np.zeros((NZ, NY, NX), bool); box[zs0:zs0 + zm, ys0:ys0 + ym, xs0:xs0 + xm] = True
+            nodes = np.flatnonzero(box.reshape(-1))            # owned nodes, x fastest inside the box
             if op == M.OP_ASSEMBLED:
                 m.set_strains(); m.homogenize(); m.assembly_jac()
-            y_loc = m.matmult(x[sl], op)
+            y_loc = m.matmult(x.reshape(-1, 3)[nodes].reshape(-1), op)
             A_loc = m.get_matrix_blocks() if op == M.OP_ASSEMBLED else None
-            got = gather_objects((u_loc, y_loc, A_loc, logs, force))
+            got = gather_objects((u_loc, y_loc, A_loc, logs, force, nodes))
             m.close()
             if rank == 0:
                 o = O.Oracle(O.Config(NX=NX, NY=NY, NZ=NZ, bc_type=bc, ts=ts, rtol=1e-12, faithful_ke=0, **extra))
                 ologs = o.run()
-                u = np.concatenate([g[0] for g in got]); y = np.concatenate([g[1] for g in got])
+                u = np.zeros(3 * NX * NY * NZ); y = np.zeros_like(u)
+                for g in got:
+                    u.reshape(-1, 3)[g[5]] = g[0].reshape(-1, 3); y.reshape(-1, 3)[g[5]] = g[1].reshape(-1, 3)
                 assert rel_err(u, o.get_vec("u")) < 1e-9, (NX, NY, NZ, bc, op, rel_err(u, o.get_vec("u")))
                 o.assembly_jac()
                 assert rel_err(y, o.matmult(x)) < 1e-13
                 if op == M.OP_ASSEMBLED:
-                    A = np.concatenate([g[2] for g in got])
+                    A = np.zeros((NX * NY * NZ, 27, 3, 3))
+                    for g in got:
+                        A[g[5]] = g[2]
                     if material == M.MAT_UNIFORM:
                         assert np.array_equal(A, o.block_stencil())
                     else:

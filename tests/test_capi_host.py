@@ -56,7 +56,7 @@ def test_partition_matches_dmda_restatement(grid, nranks):
     NX, NY, NZ = grid
     if nranks > NZ:
         pytest.skip("more ranks than planes")
-    cfg = M.Config(NX=NX, NY=NY, NZ=NZ)
+    cfg = M.Config(NX=NX, NY=NY, NZ=NZ, px=1, py=1, pz=nranks)
     o = O.Oracle(O.Config(NX=NX, NY=NY, NZ=NZ, nranks=nranks, px=1, py=1, pz=nranks))
     planes = 0
     for r in range(nranks):
@@ -71,23 +71,46 @@ def test_partition_matches_dmda_restatement(grid, nranks):
 @pytest.mark.parametrize("bc", [M.BC_BENDING, M.BC_CIRCLE])
 @pytest.mark.parametrize("nranks", [1, 2, 3])
 def test_dirichlet_lists_match_bc_init(bc, nranks):
-    kw = dict(NX=7, NY=3, NZ=8, lx=6.0, lz=7.0, bc_type=bc)
-    o = O.Oracle(O.Config(nranks=nranks, px=1, py=1, pz=nranks, **kw))
+    kw = dict(NX=7, NY=3, NZ=8, lx=6.0, lz=7.0, bc_type=bc, px=1, py=1, pz=nranks)
+    o = O.Oracle(O.Config(nranks=nranks, **kw))
     for r in range(nranks):
         idx, coef = M.bc_lists(M.Config(**kw), r, nranks)
         assert np.array_equal(idx, o.bc_list(r))
         assert set(np.unique(coef)) <= {0.0, 1.0}
     if bc == M.BC_CIRCLE:
-        idx, coef = M.bc_lists(M.Config(**kw), 0, 1)
+        idx, coef = M.bc_lists(M.Config(**dict(kw, pz=1)), 0, 1)
         assert coef.sum() > 0            # some node falls inside the circle on this grid
 
 
-def test_unsupported_decompositions_are_refused():
-    with pytest.raises(M.MacrocError) as e:
-        M.partition(M.Config(NX=8, NY=8, NZ=8, px=2), 0, 2)
-    assert e.value.code == 56
+@pytest.mark.parametrize("grid", [(5, 2, 2), (6, 4, 9), (9, 7, 8)])
+@pytest.mark.parametrize("nranks,pg", [(2, (0, 0, 0)), (3, (0, 0, 0)), (4, (0, 0, 0)), (8, (0, 0, 0)), (2, (2, 1, 1)),
+                                       (4, (2, 2, 1)), (4, (1, 2, 2)), (8, (2, 2, 2)), (6, (3, 2, 1)), (4, (0, 0, 2)),
+                                       (6, (0, 3, 0))])
+@pytest.mark.parametrize("bc", [M.BC_BENDING, M.BC_CIRCLE])
+def test_general_dmda_boxes_match_restatement(grid, nranks, pg, bc):
+    """-da_processors_x/y/z or PETSC_DECIDE: corners, ghost corners, element sizes and the
+    Dirichlet lists in PETSc's rank-contiguous global numbering (SURVEY 8f#3)."""
+    NX, NY, NZ = grid
+    kw = dict(NX=NX, NY=NY, NZ=NZ, bc_type=bc, lx=5.0, lz=6.0, px=pg[0], py=pg[1], pz=pg[2])
+    try:
+        o = O.Oracle(O.Config(nranks=nranks, **kw))
+    except ValueError:
+        with pytest.raises(M.MacrocError):
+            M.partition(M.Config(**kw), 0, nranks)
+        return
+    for r in range(nranks):
+        p = M.partition(M.Config(**kw), r, nranks)
+        assert p["corners"] == o.corners(r) and p["ghost_corners"] == o.ghost_corners(r)
+        assert p["elements_sizes"] == o.elements_sizes(r)
+        idx, coef = M.bc_lists(M.Config(**kw), r, nranks)
+        assert np.array_equal(idx, o.bc_list(r))
+
+
+def test_impossible_decompositions_are_refused():
     with pytest.raises(M.MacrocError):
-        M.partition(M.Config(NX=8, NY=8, NZ=2), 0, 3)
+        M.partition(M.Config(NX=8, NY=8, NZ=2, pz=3), 0, 3)          # more slabs than planes
+    with pytest.raises(M.MacrocError):
+        M.partition(M.Config(NX=8, NY=8, NZ=8, px=2, py=2, pz=2), 0, 4)   # 2*2*2 != 4
 
 
 def test_calc_B_host_helper():
