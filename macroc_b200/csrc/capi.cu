@@ -359,12 +359,20 @@ extern "C" int macroc_create(const macroc_config *cfg, int rank, int nranks, con
     // mask over the padded local array (ghost planes included) + (index, coef) pairs of the local
     // nodes in the owned planes; x/y ghost flags for the reductions.
     {
+        // The reference's per-rank lists are merged by PETSc (VecAssembly / MatZeroRowsColumns
+        // forward off-rank rows); the merged set equals the one-rank list, which is what the mask
+        // of the local nodes -- ghosts included -- is cut from.
         std::vector<BcEntry> ent;
         int nbcs = 0;
-        build_bc_entries(*cfg, slab, ent, &nbcs);
+        Slab whole;
+        macroc_config serial = *cfg;
+        serial.px = serial.py = serial.pz = 1;
+        make_slab(serial, 0, 1, &whole);
+        build_bc_entries(*cfg, whole, ent, &nbcs);
         std::vector<uint8_t> mask((size_t)g.S, 0);
         std::vector<int64_t> own_idx; std::vector<double> own_coef;
         for (const BcEntry &e : ent) {
+            if (e.i < slab.Xs || e.i >= slab.Xs + slab.Xm || e.j < slab.Ys || e.j >= slab.Ys + slab.Ym) continue;
             const int64_t ln = (e.i - slab.Xs) + (int64_t)slab.NX * (e.j - slab.Ys) + slab.npl * (int64_t)(e.k - slab.zs);
             const int64_t pos = g.G + ln;
             if (pos < 0 || pos >= g.S) continue;
