@@ -91,7 +91,9 @@ def gpu_mode(args):
     if world == 4:
         cases += [(12, 10, 9, M.BC_BENDING, {}, (2, 2, 1)), (11, 5, 10, M.BC_CIRCLE, dict(lx=4., lz=4.), (2, 1, 2))]
     if world == 8:
-        cases += [(12, 10, 9, M.BC_BENDING, {}, (2, 2, 2))]
+        cases += [(12, 10, 9, M.BC_BENDING, {}, (2, 2, 2)), (13, 9, 11, M.BC_CIRCLE, dict(lx=4., lz=4.), (0, 0, 0))]
+    if os.environ.get("MACROC_TEST_CASES") == "boxes":      # only the 2-D / 3-D processor grids
+        cases = [c for c in cases if sum(1 for q in c[5] if q != 1) >= 2]
     for (NX, NY, NZ, bc, extra, pg) in cases:
         for op, material in ((M.OP_ASSEMBLED, M.MAT_UNIFORM), (M.OP_MATRIX_FREE, M.MAT_UNIFORM),
                              (M.OP_ASSEMBLED, M.MAT_PER_GP)):
