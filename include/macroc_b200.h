@@ -10,11 +10,12 @@
  * returns a PetscErrorCode-style int (0 = success) and never throws.  One host
  * thread/process per GPU, like one MPI rank per DMDA sub-box in the reference.
  *
- * Vector layout at the boundary is the reference's: PETSc DMDA "natural"
- * ordering restricted to the rank's owned z-slab, dof-interleaved:
- *     v[3*((i) + NX*((j) + NY*(k - zs))) + d],  zs <= k < zs + nz_owned.
- * (With -da_processors_x 1 -da_processors_y 1 -da_processors_z P, PETSc's
- * global ordering coincides with the natural one.)
+ * Vector layout at the boundary is the reference's: the rank's part of the
+ * DMDA global vector, i.e. its owned box (macroc_partition) x fastest,
+ * dof-interleaved:
+ *     v[3*((i - xs) + xm*((j - ys) + ym*(k - zs))) + d].
+ * (With -da_processors_x 1 -da_processors_y 1 -da_processors_z P this is the
+ * natural ordering restricted to the slab.)
  *
  * There is no CPU fallback: every compute entry point fails with
  * MACROC_ERR_NO_DEVICE when no CUDA device is usable.
@@ -54,8 +55,11 @@ enum {
 /* Everything init() fixes (reference src/init.c:47-64,66-83,85-94,137-157). */
 typedef struct {
     int32_t NX, NY, NZ;            /* -da_grid_x/y/z          (macroc.h:44-46: 40, 3, 40)   */
-    int32_t px, py, pz;            /* -da_processors_x/y/z; this build shards z-slabs only:
-                                      px = py = 1 (0 = decide = 1), pz = 0 -> nranks         */
+    int32_t px, py, pz;            /* -da_processors_x/y/z; 0 = PETSC_DECIDE (PETSc's squarish
+                                      factorisation of the rank count).  Any px*py*pz = nranks
+                                      is accepted; z-slabs (1,1,P) are the fast path (halo
+                                      overlapped with the SpMV), Gauss-point arrays and VTU
+                                      output need them                                        */
     double  lx, ly, lz;            /* -lx -ly -lz             (macroc.h:47-49: 50, 1, 50)   */
     int32_t bc_type;               /* -bc_type                (init.c:64: BC_CIRCLE)        */
     int32_t ts;                    /* -ts                     (macroc.h:41: 1)              */
