@@ -570,7 +570,6 @@ extern "C" int macroc_set_strains(macroc_ctx *c, int materialize)
     if (rc) return rc;
     if (materialize || c->cfg.material == MACROC_MAT_PER_GP) {
         const Slab &s = c->slab;
-        if (s.xy_split()) FAIL(c, MACROC_ERR_UNSUPPORTED, "Gauss-point arrays need a z-slab decomposition (px = py = 1)");
         if ((rc = ensure_gp_arrays(c, false))) return rc;
         // strain of the owned elements; stress = D strain as a by-product for the uniform law
         if (c->ne_owned > 0)
@@ -612,13 +611,15 @@ extern "C" int macroc_gp_arrays(macroc_ctx *c, double **strain, double **stress,
 // host (reference AoS view, gpi = ie*8+gp) -> device SoA arrays
 static int gp_upload(macroc_ctx *c, const double *host, double *dev, int n)
 {
-    const int64_t ne = c->ne_owned;
+    const Slab &s = c->slab;
+    const int64_t ne = (int64_t)s.nex * s.ney * s.nez;           // DMDA-owned elements
     if (!host || ne == 0) return MACROC_OK;
     double *tmp = nullptr;
     CU(c, cudaMalloc(&tmp, sizeof(double) * 8 * n * (size_t)ne));
     cudaError_t e = cudaMemcpyAsync(tmp, host, sizeof(double) * 8 * n * (size_t)ne, cudaMemcpyHostToDevice, c->stream);
     if (e == cudaSuccess) {
-        LAUNCH(c, k_gp_aos_soa, cdiv64(ne * 8 * n, 256), 256, n, ne, c->er.ne_ext, tmp, dev, 1);
+        LAUNCH(c, k_gp_aos_soa, cdiv64(ne * 8 * n, 256), 256, n, (int64_t)s.nex, (int64_t)s.ney, (int64_t)s.nez, s.exs - s.Xs,
+               s.eys - s.Ys, (int64_t)s.lnex, (int64_t)s.lney, c->er.ne_ext, tmp, dev, 1);
         e = cudaStreamSynchronize(c->stream);
     }
     cudaFree(tmp);
@@ -628,11 +629,13 @@ static int gp_upload(macroc_ctx *c, const double *host, double *dev, int n)
 
 static int gp_download(macroc_ctx *c, const double *dev, double *host, int n)
 {
-    const int64_t ne = c->ne_owned;
+    const Slab &s = c->slab;
+    const int64_t ne = (int64_t)s.nex * s.ney * s.nez;           // DMDA-owned elements
     if (!host || ne == 0) return MACROC_OK;
     double *tmp = nullptr;
     CU(c, cudaMalloc(&tmp, sizeof(double) * 8 * n * (size_t)ne));
-    LAUNCH(c, k_gp_aos_soa, cdiv64(ne * 8 * n, 256), 256, n, ne, c->er.ne_ext, dev, tmp, 0);
+    LAUNCH(c, k_gp_aos_soa, cdiv64(ne * 8 * n, 256), 256, n, (int64_t)s.nex, (int64_t)s.ney, (int64_t)s.nez, s.exs - s.Xs,
+           s.eys - s.Ys, (int64_t)s.lnex, (int64_t)s.lney, c->er.ne_ext, dev, tmp, 0);
     cudaError_t e = cudaMemcpyAsync(host, tmp, sizeof(double) * 8 * n * (size_t)ne, cudaMemcpyDeviceToHost, c->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
     cudaFree(tmp);
@@ -1145,7 +1148,7 @@ extern "C" int macroc_get_strain_stress(macroc_ctx *c, double *strain, double *s
 {
     if (!c) return MACROC_ERR_ARG;
     CU(c, cudaSetDevice(c->device));
-    int64_t ne = c->ne_owned;
+    int64_t ne = (int64_t)c->slab.nex * c->slab.ney * c->slab.nez;    // DMDA-owned elements
     if (n_gp) *n_gp = ne * 8;
     if ((strain || stress) && !c->strain && ne > 0) FAIL(c, MACROC_ERR_ARG, "get_strain_stress: call set_strains(ctx, 1) first");
     int rc = gp_download(c, c->strain, strain, 6);
@@ -1162,7 +1165,6 @@ extern "C" int macroc_write_pvtu(macroc_ctx *c, const char *file_prefix)
     { int _rc = bind_constants(c); if (_rc) return _rc; }
     const Slab &s = c->slab;
     const GridDev &g = c->g;
-    if (s.xy_split()) FAIL(c, MACROC_ERR_UNSUPPORTED, "write_pvtu needs a z-slab decomposition (px = py = 1)");
     char name[4096];
     if (s.rank == 0) {
         snprintf(name, sizeof(name), "%s.pvtu", file_prefix);
@@ -1197,7 +1199,7 @@ extern "C" int macroc_write_pvtu(macroc_ctx *c, const char *file_prefix)
     // ghosted displacement (DMGlobalToLocal, output.c:150-153) and Gauss-point strain / stress
     int rc = halo_exchange(c, c->vec[V_U], c->stream);
     if (rc) return rc;
-    const int64_t N = g.npl * s.Zm, node0 = (int64_t)(s.Zs - s.zs) * g.npl;
+    const int64_t N = g.npl * s.Zm, node0 = (int64_t)(s.Zs - s.zs) * g.npl;   // the ghosted box (x/y ghosts are local nodes)
     std::vector<double> u_loc((size_t)3 * N);
     {
         double *tmp = nullptr;
@@ -1208,12 +1210,12 @@ extern "C" int macroc_write_pvtu(macroc_ctx *c, const char *file_prefix)
         cudaFree(tmp);
         if (e != cudaSuccess) FAIL(c, MACROC_ERR_CUDA, "write_pvtu: %s", cudaGetErrorString(e));
     }
-    const int64_t nelem = c->ne_owned;
+    const int64_t nelem = (int64_t)s.nex * s.ney * s.nez;                      // DMDA-owned elements
     std::vector<double> eps((size_t)48 * std::max<int64_t>(nelem, 1)), sig((size_t)48 * std::max<int64_t>(nelem, 1));
     if (c->cfg.material == MACROC_MAT_PER_GP) {
         // strain from u (output.c:219-231), stress as the material model left it (output.c:245)
         if ((rc = ensure_gp_arrays(c, false))) return rc;
-        if (nelem > 0) LAUNCH(c, k_strain_stress, cdiv64(nelem, 128), 128, g, s.ezs, s.nez, c->er.ne_ext, c->vec[V_U], c->strain, (double *)nullptr);
+        if (c->ne_owned > 0) LAUNCH(c, k_strain_stress, cdiv64(c->ne_owned, 128), 128, g, s.ezs, s.nez, c->er.ne_ext, c->vec[V_U], c->strain, (double *)nullptr);
     } else if ((rc = macroc_set_strains(c, 1)))
         return rc;
     if ((rc = gp_download(c, c->strain, eps.data(), 6))) return rc;
@@ -1230,8 +1232,8 @@ extern "C" int macroc_write_pvtu(macroc_ctx *c, const char *file_prefix)
             "<Points>\n", (int)N, (int)nelem);
     fprintf(fp, "<DataArray type=\"Float64\" Name=\"Position\" NumberOfComponents=\"3\" format=\"ascii\">\n");
     for (int k = s.Zs; k < s.Zs + s.Zm; ++k)
-        for (int j = 0; j < s.NY; ++j)
-            for (int i = 0; i < s.NX; ++i) fprintf(fp, "%01.6e\t%01.6e\t%01.6e\n", i * c->geo.dx, j * c->geo.dy, k * c->geo.dz);
+        for (int j = s.Ys; j < s.Ys + s.Ym; ++j)
+            for (int i = s.Xs; i < s.Xs + s.Xm; ++i) fprintf(fp, "%01.6e\t%01.6e\t%01.6e\n", i * c->geo.dx, j * c->geo.dy, k * c->geo.dz);
     fprintf(fp, "</DataArray>\n</Points>\n<Cells>\n");
     fprintf(fp, "<DataArray type=\"Int32\" Name=\"connectivity\" NumberOfComponents=\"1\" format=\"ascii\">\n");
     for (int ek = 0; ek < s.nez; ++ek)
@@ -1239,7 +1241,7 @@ extern "C" int macroc_write_pvtu(macroc_ctx *c, const char *file_prefix)
             for (int ei = 0; ei < s.nex; ++ei) {
                 // DMDAGetElements: local ghosted ids, counter-clockwise bottom face then top face
                 const int64_t sx = 1, sy = s.NX, sz = g.npl;
-                const int64_t b0 = ei + sy * ej + sz * (int64_t)(s.ezs + ek - s.Zs);
+                const int64_t b0 = (s.exs - s.Xs + ei) + sy * (s.eys - s.Ys + ej) + sz * (int64_t)(s.ezs + ek - s.Zs);
                 const int64_t ids[8] = {b0, b0 + sx, b0 + sx + sy, b0 + sy, b0 + sz, b0 + sx + sz, b0 + sx + sy + sz, b0 + sy + sz};
                 for (int n = 0; n < 8; ++n) fprintf(fp, "%-6d\t", (int)ids[n]);
                 fprintf(fp, "\n");

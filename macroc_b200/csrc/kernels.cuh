@@ -531,19 +531,21 @@ k_strain_stress(GridDev g, int ezs, int nez, int64_t ne_ext, const double *__res
     }
 }
 
-// AoS (gpi-major, [ie][gp][n]) <-> SoA ([(gp*n + i)][ie], pitch ne_ext) for n = 6 or 36
-__global__ void k_gp_aos_soa(int n, int64_t ne, int64_t ne_ext, const double *__restrict__ in, double *__restrict__ out,
+// AoS (gpi-major, [ie][gp][n], ie over the rank's DMDA-OWNED elements in DMDAGetElements order)
+// <-> SoA ([(gp*n + i)][le], pitch ne_ext, le over the LOCAL box's elements) for n = 6 or 36.
+// (lex0, ley0) = first owned element in local-box coordinates; for z-slabs owned == local.
+__global__ void k_gp_aos_soa(int n, int64_t onex, int64_t oney, int64_t nez, int lex0, int ley0, int64_t lnex,
+                             int64_t lney, int64_t ne_ext, const double *__restrict__ in, double *__restrict__ out,
                              int to_soa)
 {
+    const int64_t ne = onex * oney * nez;
     int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= ne * 8 * n) return;
-    if (to_soa) {           // t indexes the SoA side: coalesced writes
-        int64_t ie = t % ne, q = t / ne;
-        out[q * ne_ext + ie] = in[ie * 8 * n + q];
-    } else {                // t indexes the SoA side: coalesced reads
-        int64_t ie = t % ne, q = t / ne;
-        out[ie * 8 * n + q] = in[q * ne_ext + ie];
-    }
+    const int64_t ie = t % ne, q = t / ne;
+    const int64_t ex = ie % onex, ey = (ie / onex) % oney, ez = ie / (onex * oney);
+    const int64_t le = (lex0 + ex) + lnex * ((ley0 + ey) + lney * ez);
+    if (to_soa) out[q * ne_ext + le] = in[ie * 8 * n + q];
+    else out[ie * 8 * n + q] = in[q * ne_ext + le];
 }
 
 // one element layer of a SoA Gauss-point array <-> contiguous buffer (Gauss-point halo)

@@ -117,7 +117,19 @@ def gpu_mode(args):
                 m.set_strains(); m.homogenize(); m.assembly_jac()
             y_loc = m.matmult(x.reshape(-1, 3)[nodes].reshape(-1), op)
             A_loc = m.get_matrix_blocks() if op == M.OP_ASSEMBLED else None
-            got = gather_objects((u_loc, y_loc, A_loc, logs, force, nodes))
+            eps_loc = None
+            if material == M.MAT_UNIFORM and op == M.OP_ASSEMBLED:
+                m.set_vec(M.VEC_U, u_loc)                    # strains of the converged displacement
+                m.set_strains(materialize=True)
+                eps_loc = m.get_strain_stress()
+                import tempfile
+                with tempfile.TemporaryDirectory() as d:     # every rank writes its piece
+                    m.write_pvtu(os.path.join(d, f"sol_{NX}_{rank}"))
+                    piece = open(os.path.join(d, f"sol_{NX}_{rank}-subdo-{rank}.vtu")).read()
+                    gx, gy, gz = p["ghost_corners"][3:]
+                    ex, ey, ez = p["elements_sizes"]
+                    assert f'NumberOfPoints="{gx * gy * gz}" NumberOfCells="{ex * ey * ez}"' in piece
+            got = gather_objects((u_loc, y_loc, A_loc, logs, force, nodes, eps_loc))
             m.close()
             if rank == 0:
                 o = O.Oracle(O.Config(NX=NX, NY=NY, NZ=NZ, bc_type=bc, ts=ts, rtol=1e-12, faithful_ke=0, **extra))
@@ -141,6 +153,10 @@ def gpu_mode(args):
                 om = O.Oracle(O.Config(NX=NX, NY=NY, NZ=NZ, bc_type=bc, ts=ts, rtol=1e-12, faithful_ke=0, nranks=world,
                                        px=pg[0], py=pg[1], pz=pg[2], **extra))
                 f_ref = om.run()[-1].force
+                om.set_strains(); om.homogenize()
+                for r_, g in enumerate(got):
+                    if g[6] is not None:                     # Gauss-point export in DMDA element order
+                        assert rel_err(g[6][0], om.strain(r_)) < 1e-7 and rel_err(g[6][1], om.stress(r_)) < 1e-7, (NX, NY, NZ, pg, r_)
                 for g in got:
                     assert [l["newton_its"] for l in g[3]] == [l.newton_its for l in ologs]
                     assert g[3] == got[0][3]                 # every rank saw the same history
