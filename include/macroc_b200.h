@@ -58,8 +58,8 @@ typedef struct {
     int32_t px, py, pz;            /* -da_processors_x/y/z; 0 = PETSC_DECIDE (PETSc's squarish
                                       factorisation of the rank count).  Any px*py*pz = nranks
                                       is accepted; z-slabs (1,1,P) are the fast path (halo
-                                      overlapped with the SpMV), Gauss-point arrays and VTU
-                                      output need them                                        */
+                                      overlapped with the SpMV) and the only decomposition
+                                      for MACROC_MAT_PER_GP                                   */
     double  lx, ly, lz;            /* -lx -ly -lz             (macroc.h:47-49: 50, 1, 50)   */
     int32_t bc_type;               /* -bc_type                (init.c:64: BC_CIRCLE)        */
     int32_t ts;                    /* -ts                     (macroc.h:41: 1)              */
