@@ -197,7 +197,7 @@ def run_reference_arm(args):
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -376,7 +376,7 @@ def run_gpu_arm(args):
 
     threads = os.cpu_count() or 1
     cpu_obj = None
-    if not args.no_cpu:
+    if not args.no_cpu and world == 1:                      # reported at N=1 only (bench contract)
         cpu = CpuSample(threads)
         cpu.step(int(its_step) or 1)
         r = cpu.step(int(its_step) or 1)
@@ -412,7 +412,7 @@ def run_gpu_arm(args):
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": total_launches, "clocks": clocks, "kernels_ms": kern,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.barrier(); dist.destroy_process_group()
     return 0
@@ -427,7 +427,24 @@ def load_traffic(kernel: str):
         return None
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict):
+    """The ONE JSON line goes to the real stdout; everything else the process prints (NCCL
+    banners, library chatter) was redirected to stderr in main()."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is not None:
+        os.write(_REAL_STDOUT, data)
+    else:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
