@@ -116,6 +116,8 @@ static inline int cdiv64(int64_t a, int64_t b) { return (int)((a + b - 1) / b); 
 
 // __constant__ symbols are per device and shared by every context of the process on that
 // device; a context re-binds its element constants whenever another context used them last.
+// (Contexts are not thread-safe against each other on one device: one host thread per GPU, like
+// one MPI rank per DMDA box in the reference.)
 static uint64_t g_next_ctx_id = 1;
 static uint64_t g_const_owner[64] = {0};
 static int bind_constants(macroc_ctx *c)
@@ -733,11 +735,11 @@ extern "C" int macroc_assembly_jac(macroc_ctx *c)
                 if ((rc = halo_gp_layer(c, c->ctan, 288))) return rc;   // 8 gp x 36
             }
             const int smem = TILE_DOUBLES * (int)sizeof(double) + 27 * 32;
-            static bool configured = false;
-            if (!configured) {
+            static bool configured[64] = {false};
+            if (!configured[c->device & 63]) {
                 cudaFuncSetAttribute(k_assemble_elements<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
                 cudaFuncSetAttribute(k_assemble_elements<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-                configured = true;
+                configured[c->device & 63] = true;
             }
             int blocks = (int)std::min<int64_t>(c->g.ntiles, 148 * 3);
             if (per_gp) k_assemble_elements<true><<<blocks, 256, smem, c->stream>>>(c->g, c->er, c->geo.wg, c->ctan, c->nodemask, c->A, c->vec[V_DINV]);
@@ -756,11 +758,11 @@ static int spmv_launch_tma(macroc_ctx *c, double *p, double *w, int64_t first, i
                            bool with_dot, const int *done)
 {
     using SM = SpmvTmaSmem<WARPS, NSTAGE>;
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[64] = {false};          // function attributes are per device
+    if (!configured[c->device & 63]) {
         cudaFuncSetAttribute(k_spmv_tma<WARPS, NSTAGE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::total);
         cudaFuncSetAttribute(k_spmv_tma<WARPS, NSTAGE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::total);
-        configured = true;
+        configured[c->device & 63] = true;
     }
     int per_sm = std::max(1, (227 * 1024) / (SM::total + 1024));
     int blocks = (int)std::min<int64_t>(cdiv64(count, WARPS), (int64_t)148 * per_sm);
@@ -827,11 +829,11 @@ static int apply_operator(macroc_ctx *c, int op, double *p, double *w, bool with
             const int k0 = (int)(first / g.npl), k1 = (int)((first + count) / g.npl);
             const int tiles_x = (g.NX + MF_TX - 1) / MF_TX, tiles_y = (g.NY + MF_TY - 1) / MF_TY;
             const int64_t ntile = (int64_t)tiles_x * tiles_y * ((k1 - k0 + MF_TZ - 1) / MF_TZ);
-            static bool configured = false;
-            if (!configured) {
+            static bool configured[64] = {false};
+            if (!configured[c->device & 63]) {
                 cudaFuncSetAttribute(k_apply_mf3d<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MF_SMEM);
                 cudaFuncSetAttribute(k_apply_mf3d<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MF_SMEM);
-                configured = true;
+                configured[c->device & 63] = true;
             }
             // an odd grid: the tile -> CTA map must not be periodic in the 8 x-tiles of a row, or the
             // CTAs that always get a boundary column finish last
