@@ -13,14 +13,13 @@
 //  * residual: pass 1 writes the 24 element forces to a scratch array that is
 //    SoA over elements (coalesced), pass 2 lets every owned node add its <= 8
 //    contributions in increasing element order;
-//  * Jacobian: one CTA per 32-node operator tile, warp = (local node a of the
-//    element, half h of the block columns), lane = node.  A thread integrates 4
-//    block columns of the 3x24 row block of "its" element (the one in which the
-//    node is local node a) in registers -- only the 3x6 product B_a^T C is done
-//    by both halves -- then the warps add their blocks into the tile in shared
-//    memory in 8 conflict-free rounds (round b: block column b; within a round
-//    distinct a hit distinct stencil slots), the Dirichlet mask is applied and
-//    the tile leaves as one contiguous 62 KB store.
+//  * Jacobian: one CTA per 32-node operator tile, warp a = local node a of the
+//    element, lane = node.  Thread (a, lane) integrates the 3x24 row block of
+//    "its" element (the one in which the node is local node a) in registers --
+//    no flop is done twice -- then the 8 warps add their blocks into the tile in
+//    shared memory in 8 conflict-free rounds (round b: block column b; within a
+//    round distinct a hit distinct stencil slots), the Dirichlet mask is applied
+//    and the tile leaves as one contiguous 62 KB store.
 #pragma once
 
 #include "kernels.cuh"
@@ -137,20 +136,16 @@ k_gather_forces(GridDev g, ElemRange er, int l0, int nl, int k0, int nk, const d
     if (threadIdx.x == 0) partial[blockIdx.x] = s;
 }
 
-// General Jacobian assembly, one CTA (16 warps) per operator tile: warp = (local node a, half h),
-// lane = node.  Thread (a, h, lane) integrates block columns b in [4h, 4h+4) of the 3x24 row block
-// of the element in which its node is local node a: 36 fp64 accumulators, so two warps per
-// scheduler fit the register file (the one-thread-per-row-block version needed 245 registers).
+// General Jacobian assembly, one CTA (8 warps) per operator tile.
 template <bool PER_GP>
-__global__ void __launch_bounds__(512, 1)
+__global__ void __launch_bounds__(256)
 k_assemble_elements(GridDev g, ElemRange er, double wg, const double *__restrict__ ctan_gp,
                     const uint8_t *__restrict__ nodemask, double2 *__restrict__ A, double *__restrict__ dinv)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *tileA = reinterpret_cast<double *>(smem_raw);                  // TILE_DOUBLES
     uint8_t *nbmask = smem_raw + TILE_DOUBLES * sizeof(double);            // [27][32]
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int a = warp & 7, half = warp >> 3;
+    const int lane = threadIdx.x & 31, a = threadIdx.x >> 5;
     const int apx = node_px(a), apy = node_py(a), apz = node_pz(a);
     const int64_t per_layer = er.nex * er.ney;
 
@@ -169,11 +164,11 @@ k_assemble_elements(GridDev g, ElemRange er, double wg, const double *__restrict
         // the element in which this node is local node a
         const int ei = i - apx, ej = j - apy, ek = k - apz;
         const bool exists = valid && ei >= 0 && ei < g.NX - 1 && ej >= 0 && ej < g.NY - 1 && ek >= 0 && ek < g.NZ - 1;
-        double blk[3][12];
+        double blk[3][24];
 #pragma unroll
         for (int d = 0; d < 3; ++d)
 #pragma unroll
-            for (int q = 0; q < 12; ++q) blk[d][q] = 0.;
+            for (int q = 0; q < 24; ++q) blk[d][q] = 0.;
         if (exists) {
             const double *cg = PER_GP ? ctan_gp + ((int64_t)(ek - er.ezs) * per_layer + ei + er.nex * (int64_t)ej) : nullptr;
 #pragma unroll 1
@@ -182,41 +177,49 @@ k_assemble_elements(GridDev g, ElemRange er, double wg, const double *__restrict
                 // stream the tangent one column k at a time: T[d] = (B_a^T C)[d][k] * wg, then every
                 // block column b takes T[d] * B_b[k][.]  (B has at most two non-zeros per (k, b))
 #pragma unroll
-                for (int k6 = 0; k6 < 6; ++k6) {
+                for (int k = 0; k < 6; ++k) {
                     double ck[6];
 #pragma unroll
-                    for (int r = 0; r < 6; ++r) ck[r] = PER_GP ? __ldg(cg + (int64_t)(gp * 36 + r * 6 + k6) * er.ne_ext) : c_D[r * 6 + k6];
+                    for (int r = 0; r < 6; ++r) ck[r] = PER_GP ? __ldg(cg + (int64_t)(gp * 36 + r * 6 + k) * er.ne_ext) : c_D[r * 6 + k];
                     const double T0 = (hx * ck[0] + hy * ck[3] + hz * ck[4]) * wg;
                     const double T1 = (hy * ck[1] + hx * ck[3] + hz * ck[5]) * wg;
                     const double T2 = (hz * ck[2] + hx * ck[4] + hy * ck[5]) * wg;
 #pragma unroll
-                    for (int bb = 0; bb < 4; ++bb) {
-                        const int b = 4 * half + bb;
+                    for (int b = 0; b < 8; ++b) {
                         const double bx = c_dsh[gp][b][0], by = c_dsh[gp][b][1], bz = c_dsh[gp][b][2];
                         // column 3b+c of B: row k non-zero for (k,c) in {(0,0),(1,1),(2,2),(3,0)=by,(3,1)=bx,(4,0)=bz,(4,2)=bx,(5,1)=bz,(5,2)=by}
-                        const double v0 = k6 == 0 ? bx : (k6 == 3 ? by : (k6 == 4 ? bz : 0.));
-                        const double v1 = k6 == 1 ? by : (k6 == 3 ? bx : (k6 == 5 ? bz : 0.));
-                        const double v2 = k6 == 2 ? bz : (k6 == 4 ? bx : (k6 == 5 ? by : 0.));
-                        if (k6 == 0 || k6 == 3 || k6 == 4) { blk[0][3 * bb + 0] = fma(T0, v0, blk[0][3 * bb + 0]); blk[1][3 * bb + 0] = fma(T1, v0, blk[1][3 * bb + 0]); blk[2][3 * bb + 0] = fma(T2, v0, blk[2][3 * bb + 0]); }
-                        if (k6 == 1 || k6 == 3 || k6 == 5) { blk[0][3 * bb + 1] = fma(T0, v1, blk[0][3 * bb + 1]); blk[1][3 * bb + 1] = fma(T1, v1, blk[1][3 * bb + 1]); blk[2][3 * bb + 1] = fma(T2, v1, blk[2][3 * bb + 1]); }
-                        if (k6 == 2 || k6 == 4 || k6 == 5) { blk[0][3 * bb + 2] = fma(T0, v2, blk[0][3 * bb + 2]); blk[1][3 * bb + 2] = fma(T1, v2, blk[1][3 * bb + 2]); blk[2][3 * bb + 2] = fma(T2, v2, blk[2][3 * bb + 2]); }
+                        if (k == 0) { blk[0][3 * b + 0] = fma(T0, bx, blk[0][3 * b + 0]); blk[1][3 * b + 0] = fma(T1, bx, blk[1][3 * b + 0]); blk[2][3 * b + 0] = fma(T2, bx, blk[2][3 * b + 0]); }
+                        if (k == 1) { blk[0][3 * b + 1] = fma(T0, by, blk[0][3 * b + 1]); blk[1][3 * b + 1] = fma(T1, by, blk[1][3 * b + 1]); blk[2][3 * b + 1] = fma(T2, by, blk[2][3 * b + 1]); }
+                        if (k == 2) { blk[0][3 * b + 2] = fma(T0, bz, blk[0][3 * b + 2]); blk[1][3 * b + 2] = fma(T1, bz, blk[1][3 * b + 2]); blk[2][3 * b + 2] = fma(T2, bz, blk[2][3 * b + 2]); }
+                        if (k == 3) {
+                            blk[0][3 * b + 0] = fma(T0, by, blk[0][3 * b + 0]); blk[1][3 * b + 0] = fma(T1, by, blk[1][3 * b + 0]); blk[2][3 * b + 0] = fma(T2, by, blk[2][3 * b + 0]);
+                            blk[0][3 * b + 1] = fma(T0, bx, blk[0][3 * b + 1]); blk[1][3 * b + 1] = fma(T1, bx, blk[1][3 * b + 1]); blk[2][3 * b + 1] = fma(T2, bx, blk[2][3 * b + 1]);
+                        }
+                        if (k == 4) {
+                            blk[0][3 * b + 0] = fma(T0, bz, blk[0][3 * b + 0]); blk[1][3 * b + 0] = fma(T1, bz, blk[1][3 * b + 0]); blk[2][3 * b + 0] = fma(T2, bz, blk[2][3 * b + 0]);
+                            blk[0][3 * b + 2] = fma(T0, bx, blk[0][3 * b + 2]); blk[1][3 * b + 2] = fma(T1, bx, blk[1][3 * b + 2]); blk[2][3 * b + 2] = fma(T2, bx, blk[2][3 * b + 2]);
+                        }
+                        if (k == 5) {
+                            blk[0][3 * b + 1] = fma(T0, bz, blk[0][3 * b + 1]); blk[1][3 * b + 1] = fma(T1, bz, blk[1][3 * b + 1]); blk[2][3 * b + 1] = fma(T2, bz, blk[2][3 * b + 1]);
+                            blk[0][3 * b + 2] = fma(T0, by, blk[0][3 * b + 2]); blk[1][3 * b + 2] = fma(T1, by, blk[1][3 * b + 2]); blk[2][3 * b + 2] = fma(T2, by, blk[2][3 * b + 2]);
+                        }
                     }
                 }
             }
         }
         __syncthreads();
-        // 8 rounds: in round b the 8 warps that hold block column b add it; for a fixed b the 8
-        // warps (different a) target 8 different slots, so no two threads touch the same entry
+        // 8 rounds: in round b every warp adds block column b; for a fixed b the 8 warps
+        // (different a) target 8 different slots, so no two threads touch the same entry
 #pragma unroll
         for (int b = 0; b < 8; ++b) {
-            if (exists && (b >> 2) == half) {
+            if (exists) {
                 const int slot = (node_pz(b) - apz + 1) * 9 + (node_py(b) - apy + 1) * 3 + (node_px(b) - apx + 1);
 #pragma unroll
                 for (int d = 0; d < 3; ++d)
 #pragma unroll
                     for (int cc = 0; cc < 3; ++cc) {
                         const int kk = slot * 9 + 3 * d + cc;
-                        tileA[((kk >> 1) * TILE_NODES + lane) * 2 + (kk & 1)] += blk[d][3 * (b & 3) + cc];
+                        tileA[((kk >> 1) * TILE_NODES + lane) * 2 + (kk & 1)] += blk[d][3 * b + cc];
                     }
             }
             __syncthreads();

@@ -742,8 +742,8 @@ extern "C" int macroc_assembly_jac(macroc_ctx *c)
                 configured[c->device & 63] = true;
             }
             int blocks = (int)std::min<int64_t>(c->g.ntiles, 148 * 3);
-            if (per_gp) k_assemble_elements<true><<<blocks, 512, smem, c->stream>>>(c->g, c->er, c->geo.wg, c->ctan, c->nodemask, c->A, c->vec[V_DINV]);
-            else k_assemble_elements<false><<<blocks, 512, smem, c->stream>>>(c->g, c->er, c->geo.wg, c->ctan, c->nodemask, c->A, c->vec[V_DINV]);
+            if (per_gp) k_assemble_elements<true><<<blocks, 256, smem, c->stream>>>(c->g, c->er, c->geo.wg, c->ctan, c->nodemask, c->A, c->vec[V_DINV]);
+            else k_assemble_elements<false><<<blocks, 256, smem, c->stream>>>(c->g, c->er, c->geo.wg, c->ctan, c->nodemask, c->A, c->vec[V_DINV]);
             c->launches++;
         } else
             LAUNCH(c, k_fill_operator, cdiv64(c->g.ntiles, 8), 256, c->g, c->T, c->nodemask, c->A, c->vec[V_DINV]);
