@@ -837,9 +837,9 @@ static int apply_operator(macroc_ctx *c, int op, double *p, double *w, bool with
             }
             // an odd grid: the tile -> CTA map must not be periodic in the 8 x-tiles of a row, or the
             // CTAs that always get a boundary column finish last
-            blocks = (int)std::min<int64_t>(ntile, 148 * 4 - 1);
-            if (with_dot) k_apply_mf3d<true><<<blocks, MF_THREADS, MF_SMEM, c->stream>>>(g, c->nodemask, p, w, k0, k1, tiles_x, tiles_y, c->partial + nparts, done);
-            else k_apply_mf3d<false><<<blocks, MF_THREADS, MF_SMEM, c->stream>>>(g, c->nodemask, p, w, k0, k1, tiles_x, tiles_y, c->partial + nparts, done);
+            blocks = (int)std::min<int64_t>(ntile, 148 * 6 - 1);
+            if (with_dot) k_apply_mf3d<true><<<blocks, MF_THREADS, MF_SMEM, c->stream>>>(g, c->T, c->nodemask, p, w, k0, k1, tiles_x, tiles_y, c->partial + nparts, done);
+            else k_apply_mf3d<false><<<blocks, MF_THREADS, MF_SMEM, c->stream>>>(g, c->T, c->nodemask, p, w, k0, k1, tiles_x, tiles_y, c->partial + nparts, done);
             c->launches++;
         } else {
             blocks = spmv_launch(c, p, w, first, count, c->partial + nparts, with_dot, done);

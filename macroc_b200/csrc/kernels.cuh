@@ -304,19 +304,18 @@ constexpr int MF_PX = MF_TX + 4, MF_PY = MF_TY + 2, MF_PZ = MF_TZ + 2;
 static_assert((MF_PX * MF_PY) % 16 == 8, "bank-conflict-free z pitch");
 constexpr int MF_PATCH = MF_PX * MF_PY * MF_PZ;
 constexpr int MF_THREADS = MF_TX * MF_TZ;
-constexpr int MF_SMEM = (3 * MF_PATCH + 27 * 243) * (int)sizeof(double);   // patch + class table
+constexpr int MF_SMEM = 3 * MF_PATCH * (int)sizeof(double);   // the staged patch of M x
 
 template <bool DOT>
-__global__ void __launch_bounds__(MF_THREADS)
-k_apply_mf3d(GridDev g, const uint8_t *__restrict__ nodemask, const double *__restrict__ x, double *__restrict__ y,
+__global__ void __launch_bounds__(MF_THREADS, 3)
+k_apply_mf3d(GridDev g, const double *__restrict__ Tg, const uint8_t *__restrict__ nodemask,
+             const double *__restrict__ x, double *__restrict__ y,
              int k0, int k1, int tiles_x, int tiles_y, double *__restrict__ partial, const int *__restrict__ done)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double(*sx)[MF_PATCH] = reinterpret_cast<double(*)[MF_PATCH]>(smem_raw);
-    double *sT = reinterpret_cast<double *>(smem_raw) + 3 * MF_PATCH;    // class stencils for boundary warps
     __shared__ double sm[8];
     if (done && *done) return;
-    for (int q = threadIdx.x; q < 27 * 243; q += MF_THREADS) sT[q] = c_T[q];
     // warp w = x-block (w % 4) of 8 nodes, z-block (w / 4) of 4 planes; lane = 8 (x) x 4 (z): only
     // 2 of the 32 x-blocks of a row touch the x faces (a 32-wide warp would put 2 of 8 there)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -389,8 +388,8 @@ k_apply_mf3d(GridDev g, const uint8_t *__restrict__ nodemask, const double *__re
                         }
                     }
         } else {
-            // boundary classes: per-node class offsets into the shared-memory copy of the table
-            // (lanes of one class broadcast; divergent constant-bank reads would serialise)
+            // boundary classes: per-node class offsets into the global copy of the table (L1
+            // resident; lanes of one class broadcast, divergent constant-bank reads would serialise)
 #pragma unroll 1
             for (int dz = -1; dz <= 1; ++dz)
 #pragma unroll 1
@@ -403,10 +402,10 @@ k_apply_mf3d(GridDev g, const uint8_t *__restrict__ nodemask, const double *__re
                         for (int jj = 0; jj < MF_TY; ++jj) {
                             const int ddy = py - 1 - jj;
                             if (ddy < -1 || ddy > 1) continue;
-                            const double *m = sT + type[jj] * 243 + ((dz + 1) * 9 + (ddy + 1) * 3 + (dx + 1)) * 9;
-                            acc[jj][0] = fma(m[0], x0, acc[jj][0]); acc[jj][0] = fma(m[1], x1, acc[jj][0]); acc[jj][0] = fma(m[2], x2, acc[jj][0]);
-                            acc[jj][1] = fma(m[3], x0, acc[jj][1]); acc[jj][1] = fma(m[4], x1, acc[jj][1]); acc[jj][1] = fma(m[5], x2, acc[jj][1]);
-                            acc[jj][2] = fma(m[6], x0, acc[jj][2]); acc[jj][2] = fma(m[7], x1, acc[jj][2]); acc[jj][2] = fma(m[8], x2, acc[jj][2]);
+                            const double *m = Tg + type[jj] * 243 + ((dz + 1) * 9 + (ddy + 1) * 3 + (dx + 1)) * 9;
+                            acc[jj][0] = fma(__ldg(m + 0), x0, acc[jj][0]); acc[jj][0] = fma(__ldg(m + 1), x1, acc[jj][0]); acc[jj][0] = fma(__ldg(m + 2), x2, acc[jj][0]);
+                            acc[jj][1] = fma(__ldg(m + 3), x0, acc[jj][1]); acc[jj][1] = fma(__ldg(m + 4), x1, acc[jj][1]); acc[jj][1] = fma(__ldg(m + 5), x2, acc[jj][1]);
+                            acc[jj][2] = fma(__ldg(m + 6), x0, acc[jj][2]); acc[jj][2] = fma(__ldg(m + 7), x1, acc[jj][2]); acc[jj][2] = fma(__ldg(m + 8), x2, acc[jj][2]);
                         }
                     }
         }
