@@ -58,8 +58,7 @@ typedef struct {
     int32_t px, py, pz;            /* -da_processors_x/y/z; 0 = PETSC_DECIDE (PETSc's squarish
                                       factorisation of the rank count).  Any px*py*pz = nranks
                                       is accepted; z-slabs (1,1,P) are the fast path (halo
-                                      overlapped with the SpMV) and the only decomposition
-                                      for MACROC_MAT_PER_GP                                   */
+                                      overlapped with the SpMV)                               */
     double  lx, ly, lz;            /* -lx -ly -lz             (macroc.h:47-49: 50, 1, 50)   */
     int32_t bc_type;               /* -bc_type                (init.c:64: BC_CIRCLE)        */
     int32_t ts;                    /* -ts                     (macroc.h:41: 1)              */
@@ -128,9 +127,12 @@ int macroc_homogenize(macroc_ctx *ctx);
  * reference exchanges with MicroPP at gpi = ie*8+gp, assembly.c:58,91,148).  On the device they
  * are SoA over elements so that consecutive lanes touch consecutive doubles:
  *     strain/stress[(gp*6 + i) * pitch + ie],   ctan[((gp*6 + k)*6 + l) * pitch + ie],
- * ie = rank-local element in DMDAGetElements order, pitch returned in *pitch (>= n_gp/8; the
- * tail holds the upper neighbour's first element layer).  A GPU material model reads strain
- * and writes stress and ctan in place. */
+ * ie = element of the rank's local box, ie = ex + lnex*(ey + lney*ez) with lnex, lney the local
+ * box's elements per row / rows per layer (ghosted node extents of macroc_partition minus one);
+ * the DMDA-owned elements are ex < nex, ey < ney, ez < nez (for z-slabs: all of them, in
+ * DMDAGetElements order); the extra layers belong to the upper neighbours and are refreshed by
+ * Gauss-point halos.  pitch is returned in *pitch, *n_gp = 8 * lnex*lney*nez.  A GPU material
+ * model reads strain and writes stress and ctan of the owned elements in place. */
 int macroc_gp_arrays(macroc_ctx *ctx, double **strain, double **stress, double **ctan, int64_t *n_gp,
                      int64_t *pitch);
 /* host -> device copies into those arrays in the reference's AoS view, stress[gpi*6 + i],

@@ -291,8 +291,6 @@ extern "C" int macroc_create(const macroc_config *cfg, int rank, int nranks, con
     Slab slab;
     int rc = make_slab(*cfg, rank, nranks, &slab);
     if (rc) FAIL((macroc_ctx *)nullptr, rc, "macroc_create: -da_processors_x/y/z do not factor the rank count or exceed the grid");
-    if (slab.xy_split() && cfg->material == MACROC_MAT_PER_GP)
-        FAIL((macroc_ctx *)nullptr, MACROC_ERR_UNSUPPORTED, "macroc_create: per-Gauss-point material arrays need a z-slab decomposition (px = py = 1)");
     if (cfg->bc_type != MACROC_BC_BENDING && cfg->bc_type != MACROC_BC_CIRCLE)
         FAIL((macroc_ctx *)nullptr, MACROC_ERR_ARG, "macroc_create: bc_type must be 0 or 1");
     if (nranks > 1 && !id128) FAIL((macroc_ctx *)nullptr, MACROC_ERR_ARG, "macroc_create: nranks > 1 needs a unique id");
@@ -543,23 +541,34 @@ static int ensure_gp_arrays(macroc_ctx *c, bool need_ctan)
     return MACROC_OK;
 }
 
-// Gauss-point halo: the first owned element layer of rank r+1 is the layer above rank r's
-// top node plane; rank r keeps a copy behind its owned layers (layer index nez).  The arrays
-// are SoA over elements, so a layer is packed into / unpacked from a contiguous buffer.
+// Gauss-point halo.  The local box holds, beside the DMDA-owned elements, the first owned
+// element layer of every upper neighbour (x+, y+, z+): the layer the gather-form assembly
+// integrates redundantly.  Three phases (x, y, z; a phase sends layer 0 along its axis over the
+// full local extent of the other two, ghosts received earlier included), so edge and corner
+// elements arrive without diagonal messages.  The arrays are SoA over elements: a layer is
+// packed into / unpacked from a contiguous buffer.
 static int halo_gp_layer(macroc_ctx *c, double *arr, int nq)
 {
     if (!c->comm) return MACROC_OK;
     const Slab &s = c->slab;
-    const int64_t per_layer = (int64_t)s.lnex * s.lney;
-    const size_t cnt = (size_t)per_layer * nq;
-    if (!c->gp_halo) CU(c, cudaMalloc(&c->gp_halo, sizeof(double) * 2 * (size_t)per_layer * 288));
-    double *sbuf = c->gp_halo, *rbuf = c->gp_halo + (size_t)per_layer * 288;
-    if (s.has_lower()) LAUNCH(c, k_gp_layer_copy, cdiv64(cnt, 256), 256, nq, per_layer, c->er.ne_ext, (int64_t)0, arr, sbuf, 1);
-    NC(c, ncclGroupStart());
-    if (s.has_lower()) NC(c, ncclSend(sbuf, cnt, ncclDouble, s.nb[4], c->comm, c->stream));
-    if (s.has_upper()) NC(c, ncclRecv(rbuf, cnt, ncclDouble, s.nb[5], c->comm, c->stream));
-    NC(c, ncclGroupEnd());
-    if (s.has_upper()) LAUNCH(c, k_gp_layer_copy, cdiv64(cnt, 256), 256, nq, per_layer, c->er.ne_ext, c->ne_owned, arr, rbuf, 0);
+    const int64_t lnex = s.lnex, lney = s.lney, nlay = c->er.nez_ext;
+    const int64_t maxface = std::max({lney * nlay, lnex * nlay, lnex * lney});
+    if (!c->gp_halo) CU(c, cudaMalloc(&c->gp_halo, sizeof(double) * 2 * (size_t)maxface * 288));
+    double *sbuf = c->gp_halo, *rbuf = c->gp_halo + (size_t)maxface * 288;
+    const int64_t owned[3] = {s.nex, s.ney, s.nez};          // DMDA-owned element layers per axis
+    for (int axis = 0; axis < 3; ++axis) {
+        const int lo = s.nb[2 * axis], hi = s.nb[2 * axis + 1];
+        if (lo < 0 && hi < 0) continue;
+        const int64_t face = axis == 0 ? lney * nlay : (axis == 1 ? lnex * nlay : lnex * lney);
+        const size_t cnt = (size_t)face * nq;
+        const int blocks = cdiv64((int64_t)cnt, 256);
+        if (lo >= 0) LAUNCH(c, k_gp_face_copy, blocks, 256, nq, lnex, lney, nlay, axis, (int64_t)0, c->er.ne_ext, arr, sbuf, 1);
+        NC(c, ncclGroupStart());
+        if (lo >= 0) NC(c, ncclSend(sbuf, cnt, ncclDouble, lo, c->comm, c->stream));
+        if (hi >= 0) NC(c, ncclRecv(rbuf, cnt, ncclDouble, hi, c->comm, c->stream));
+        NC(c, ncclGroupEnd());
+        if (hi >= 0) LAUNCH(c, k_gp_face_copy, blocks, 256, nq, lnex, lney, nlay, axis, owned[axis], c->er.ne_ext, arr, rbuf, 0);
+    }
     return MACROC_OK;
 }
 

@@ -547,15 +547,23 @@ __global__ void k_gp_aos_soa(int n, int64_t onex, int64_t oney, int64_t nez, int
     else out[ie * 8 * n + q] = in[q * ne_ext + le];
 }
 
-// one element layer of a SoA Gauss-point array <-> contiguous buffer (Gauss-point halo)
-__global__ void k_gp_layer_copy(int nq, int64_t per_layer, int64_t ne_ext, int64_t layer_off, double *__restrict__ arr,
-                                double *__restrict__ buf, int pack)
+// one element layer (normal to `axis`) of a SoA Gauss-point array <-> contiguous buffer
+// (Gauss-point halo).  Local elements are indexed ex + lnex*(ey + lney*ez), ez < nlay.
+__global__ void k_gp_face_copy(int nq, int64_t lnex, int64_t lney, int64_t nlay, int axis, int64_t layer,
+                               int64_t ne_ext, double *__restrict__ arr, double *__restrict__ buf, int pack)
 {
+    const int64_t d0 = axis == 0 ? lney : lnex, d1 = axis == 2 ? lney : nlay;   // the two in-face extents
+    const int64_t face = d0 * d1;
     int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= per_layer * nq) return;
-    int64_t x = t % per_layer, q = t / per_layer;
-    if (pack) buf[t] = arr[q * ne_ext + layer_off + x];
-    else arr[q * ne_ext + layer_off + x] = buf[t];
+    if (t >= face * nq) return;
+    const int64_t f = t % face, q = t / face, a0 = f % d0, a1 = f / d0;
+    int64_t ex, ey, ez;
+    if (axis == 0) { ex = layer; ey = a0; ez = a1; }
+    else if (axis == 1) { ex = a0; ey = layer; ez = a1; }
+    else { ex = a0; ey = a1; ez = layer; }
+    const int64_t e = ex + lnex * (ey + lney * ez);
+    if (pack) buf[t] = arr[q * ne_ext + e];
+    else arr[q * ne_ext + e] = buf[t];
 }
 
 // forces.c:58-106 / :115-166: sum of the 8 Gauss-point stresses of the elements

@@ -97,8 +97,6 @@ def gpu_mode(args):
     for (NX, NY, NZ, bc, extra, pg) in cases:
         for op, material in ((M.OP_ASSEMBLED, M.MAT_UNIFORM), (M.OP_MATRIX_FREE, M.MAT_UNIFORM),
                              (M.OP_ASSEMBLED, M.MAT_PER_GP)):
-            if material == M.MAT_PER_GP and pg != zs:
-                continue                                     # Gauss-point arrays: z-slabs only
             box = [M.get_unique_id() if rank == 0 else None]
             dist.broadcast_object_list(box, src=0)
             ts = 3
