@@ -33,13 +33,16 @@ struct ElemRange {
     int64_t ne_ext;   // stored elements = pitch of the SoA Gauss-point arrays
 };
 
-// MicroPP stand-in on the device: sigma = D eps, C = D for every Gauss point of the owned
-// elements (SoA arrays, pitch ne_ext).
-__global__ void k_homogenize_linear(int64_t ne, int64_t ne_ext, const double *__restrict__ strain,
-                                    double *__restrict__ stress, double *__restrict__ ctan)
+// MicroPP stand-in on the device: sigma = D eps, C = D for every Gauss point of the DMDA-owned
+// elements only (ex < onex, ey < oney), like a real material model; the upper neighbours'
+// layers arrive through the Gauss-point halo.  SoA arrays, pitch ne_ext.
+__global__ void k_homogenize_linear(int64_t ne, int64_t lnex, int64_t lney, int64_t onex, int64_t oney, int64_t ne_ext,
+                                    const double *__restrict__ strain, double *__restrict__ stress,
+                                    double *__restrict__ ctan)
 {
     int64_t ie = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (ie >= ne) return;
+    if (ie % lnex >= onex || (ie / lnex) % lney >= oney) return;
 #pragma unroll 1
     for (int gp = 0; gp < 8; ++gp) {
         double e[6];

@@ -599,7 +599,9 @@ extern "C" int macroc_homogenize(macroc_ctx *c)
     { int _rc = bind_constants(c); if (_rc) return _rc; }
     int rc = ensure_gp_arrays(c, true);
     if (rc) return rc;
-    if (c->ne_owned > 0) LAUNCH(c, k_homogenize_linear, cdiv64(c->ne_owned, 128), 128, c->ne_owned, c->er.ne_ext, c->strain, c->stress, c->ctan);
+    if (c->ne_owned > 0)
+        LAUNCH(c, k_homogenize_linear, cdiv64(c->ne_owned, 128), 128, c->ne_owned, (int64_t)c->slab.lnex, (int64_t)c->slab.lney,
+               (int64_t)c->slab.nex, (int64_t)c->slab.ney, c->er.ne_ext, c->strain, c->stress, c->ctan);
     CU(c, cudaGetLastError());
     return MACROC_OK;
 }
