@@ -372,3 +372,24 @@ def test_vtu_output_matches_reference_files(tmp_path, monkeypatch):
                     assert float(xs) == pytest.approx(float(ys), rel=2e-5, abs=2e-5 * scale + 1e-300), (a[:80], b[:80])
                 else:
                     assert xs == ys, (a[:120], b[:120])
+
+
+def test_ksp_termination_paths():
+    """KSPConvergedDefault / KSPSolve_CG exits other than the relative tolerance: zero right-hand
+    side (0 iterations, CONVERGED_ATOL), iteration limit (DIVERGED_ITS with its == maxits)."""
+    kw = dict(NX=12, NY=5, NZ=6, bc_type=M.BC_BENDING, lx=10., ly=1., lz=1.)
+    m = M.MacroC(M.Config(ksp_maxits=7, **kw))
+    o = O.Oracle(O.Config(maxits=7, faithful_ke=0, **kw))
+    m.set_strains(); m.assembly_res(); m.assembly_jac()            # u = 0 -> b = 0
+    o.set_strains(); o.homogenize(); o.assembly_res(); o.assembly_jac()
+    assert m.solve_Ax() == (0, 0.0) and m.ksp_reason() == 3
+    assert o.solve()[0] == 0
+    for p in (m, o):
+        p.apply_bc_on_u(-1e-3); p.set_strains()
+        if p is o:
+            p.homogenize()
+        p.assembly_res()
+    its_m, rn_m = m.solve_Ax(); its_o, rn_o = o.solve()
+    assert its_m == its_o == 7 and m.ksp_reason() == -3
+    assert rn_m == pytest.approx(rn_o, rel=1e-9)
+    assert rel_err(m.get_vec(M.VEC_DU), o.get_vec("du")) < 1e-10     # same 7 iterates
