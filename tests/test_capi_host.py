@@ -133,3 +133,32 @@ def test_product_does_not_reference_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".c", ".cpp")) or f == "Makefile":
                 txt = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "oracle" not in txt.lower(), f"{f} mentions the oracle"
+
+
+def test_header_is_plain_c99(tmp_path):
+    """The drop-in boundary must be includable from C (the reference is a C99 project)."""
+    import subprocess
+    src = tmp_path / "use_header.c"
+    src.write_text('#include "macroc_b200.h"\n'
+                   "int main(void) { macroc_config c; macroc_ctx *x = 0; (void)x;\n"
+                   "  return macroc_default_config(&c) + (int)sizeof(c.D) - 288; }\n")
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+                        "-c", str(src), "-o", str(tmp_path / "use_header.o")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+
+
+def test_config_struct_layout_matches_ctypes_mirror(tmp_path):
+    """sizeof / offsets of macroc_config as the C compiler sees them == the ctypes mirror."""
+    import subprocess
+    src = tmp_path / "layout.c"
+    fields = ["NX", "px", "lx", "bc_type", "ts", "vtu_freq", "dt", "newton_max_its", "newton_min_tol", "ksp_rtol",
+              "ksp_maxits", "E", "D", "use_D", "op", "device", "material", "jac_mode"]
+    body = "".join(f'  printf("{f} %zu\\n", offsetof(macroc_config, {f}));\n' for f in fields)
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "macroc_b200.h"\nint main(void) {\n'
+                   '  printf("sizeof %zu\\n", sizeof(macroc_config));\n' + body + "  return 0; }\n")
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = dict(l.split() for l in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    assert int(out["sizeof"]) == C.sizeof(capi.CConfig)
+    for f in fields:
+        assert int(out[f]) == getattr(capi.CConfig, f).offset, f

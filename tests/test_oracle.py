@@ -225,3 +225,16 @@ def test_oracle_log_equals_live_reference_run(flags):
         pick = lambda t: [l for l in t.splitlines() if re.match(r"(\|RES\||KSP :|Newton Iteration|Time Step)", l)]
         assert pick(ref) == pick(mine)
         assert np.array_equal(np.fromfile(os.path.join(d, "dump_vec0.bin")), o.get_vec("u"))
+
+
+def test_openmp_mode_equals_strict_mode():
+    """bench.py times the oracle with nthreads > 1 (ranks as threads): same operator and residual,
+    solution to rounding (parallel reductions reorder the dot products)."""
+    kw = dict(NX=12, NY=6, NZ=9, bc_type=0, ts=2, lx=10., ly=1., lz=1.)
+    a = O.Oracle(O.Config(nranks=1, nthreads=1, **kw))
+    b = O.Oracle(O.Config(nranks=3, px=1, py=1, pz=3, nthreads=3, **kw))
+    la, lb = a.run(), b.run()
+    assert [l.newton_its for l in la] == [l.newton_its for l in lb]
+    assert rel_err(b.block_stencil(), a.block_stencil()) < 1e-14
+    assert rel_err(b.get_vec("u"), a.get_vec("u")) < 1e-8
+    assert b.time_cg_iterations(2) > 0
