@@ -79,7 +79,10 @@ typedef struct {
     int32_t device;                /* CUDA device ordinal, -1 = current                      */
     int32_t material;              /* MACROC_MAT_*                                           */
     int32_t jac_mode;              /* MACROC_JAC_*                                           */
-    int32_t reserved[6];
+    int32_t physical_B;            /* 0 (default): the reference's calc_B, whose local dx=dy=dz=1
+                                      makes B that of a unit cube (assembly.c:198); 1: B of the
+                                      physical element (-physical_B 1)                       */
+    int32_t reserved[5];
 } macroc_config;
 
 typedef struct macroc_ctx macroc_ctx;

@@ -411,7 +411,8 @@ extern "C" int macroc_create(const macroc_config *cfg, int rank, int nranks, con
         CUC(cudaMalloc(&c->consts, sizeof(double) * (228 + 27 * 243)));
         CUC(cudaMemcpyAsync(c->consts + 192, D, sizeof(D), cudaMemcpyHostToDevice, c->stream));
         CUC(cudaMemcpyToSymbolAsync(c_D, D, sizeof(D), 0, cudaMemcpyHostToDevice, c->stream));
-        LAUNCH(c, k_make_dsh, 1, 64, c->consts);
+        const bool phys = cfg->physical_B != 0;
+        LAUNCH(c, k_make_dsh, 1, 64, c->consts, phys ? c->geo.dx : 1., phys ? c->geo.dy : 1., phys ? c->geo.dz : 1.);
         CUC(cudaMemcpyToSymbolAsync(c_dsh, c->consts, sizeof(double) * 192, 0, cudaMemcpyDeviceToDevice, c->stream));
         LAUNCH(c, k_element_matrix, 3, 192, c->geo.wg, c->Ke);
         LAUNCH(c, k_stencil_table, cdiv64(27 * 243, 256), 256, c->Ke, c->T);

@@ -86,7 +86,7 @@ __device__ __forceinline__ double block_sum(double v, double *sm)
 
 // calc_B's dsh table (assembly.c:195-232) with explicit round-to-nearest ops so
 // the bits match the CPU evaluation of the same expressions.
-__global__ void k_make_dsh(double *out /* [8][8][3] */)
+__global__ void k_make_dsh(double *out /* [8][8][3] */, double hx, double hy, double hz)
 {
     int t = threadIdx.x;
     if (t >= 64) return;
@@ -95,9 +95,10 @@ __global__ void k_make_dsh(double *out /* [8][8][3] */)
     double xi = c_sgn[gp][0] * CONSTXG, eta = c_sgn[gp][1] * CONSTXG, zeta = c_sgn[gp][2] * CONSTXG;
     double fx = __dadd_rn(1., c_sgn[n][0] * xi), fy = __dadd_rn(1., c_sgn[n][1] * eta),
            fz = __dadd_rn(1., c_sgn[n][2] * zeta);
-    out[(gp * 8 + n) * 3 + 0] = c_sgn[n][0] * __dmul_rn(fy, fz) / 8. * 2.;
-    out[(gp * 8 + n) * 3 + 1] = c_sgn[n][1] * __dmul_rn(fx, fz) / 8. * 2.;
-    out[(gp * 8 + n) * 3 + 2] = c_sgn[n][2] * __dmul_rn(fx, fy) / 8. * 2.;
+    // hx = hy = hz = 1 reproduces the reference (assembly.c:198 shadows the global dx, dy, dz)
+    out[(gp * 8 + n) * 3 + 0] = __ddiv_rn(c_sgn[n][0] * __dmul_rn(fy, fz) / 8. * 2., hx);
+    out[(gp * 8 + n) * 3 + 1] = __ddiv_rn(c_sgn[n][1] * __dmul_rn(fx, fz) / 8. * 2., hy);
+    out[(gp * 8 + n) * 3 + 2] = __ddiv_rn(c_sgn[n][2] * __dmul_rn(fx, fy) / 8. * 2., hz);
 }
 
 __device__ __forceinline__ double Bentry(int gp, int row, int col)

@@ -92,9 +92,13 @@ void orc_default_config(orc_config *cfg)
 
 /* assembly.c:195-254.  Note the local dx=dy=dz=1 at :198: B is that of a unit
  * cube whatever lx/NX is. */
+/* element edge lengths seen by calc_B: 1,1,1 = the reference (assembly.c:198); the physical
+ * dx,dy,dz when a context is created with physical_B (named switch) */
+static double g_elem_h[3] = {1., 1., 1.};
+
 void orc_calc_B(int gp, double *B)
 {
-    const double hx = 1., hy = 1., hz = 1.;
+    const double hx = g_elem_h[0], hy = g_elem_h[1], hz = g_elem_h[2];
     double xi = SGN[gp][0] * CONSTXG, eta = SGN[gp][1] * CONSTXG, zeta = SGN[gp][2] * CONSTXG;
     double dsh[NPE][DIM];
     for (int n = 0; n < NPE; ++n) {
@@ -443,6 +447,7 @@ orc_ctx *orc_create(const orc_config *cfg)
     c->wg = c->dx * c->dy * c->dz / NPE;
     c->rad = 1.;
     orc_isotropic_D(cfg->E, cfg->nu, c->D);
+    g_elem_h[0] = cfg->physical_B ? c->dx : 1.; g_elem_h[1] = cfg->physical_B ? c->dy : 1.; g_elem_h[2] = cfg->physical_B ? c->dz : 1.;
     for (int r = 0; r < c->nranks; ++r) { setup_l2g(c, r); bc_init(c, &c->rk[r]); }
     build_pattern(c);
     c->u = (double *)calloc((size_t)c->ndof, sizeof(double));

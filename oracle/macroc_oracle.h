@@ -60,6 +60,8 @@ typedef struct {
                                   4-deep loop (assembly.c:94-99); 0: reuse Ae while
                                   the 8 tangents are bitwise identical (same bits) */
     int nthreads;              /* 1: strict reference order; >1: OpenMP (timing)   */
+    int physical_B;            /* 0: reference quirk, calc_B's local dx=dy=dz=1 (assembly.c:198);
+                                  1: B of the physical element (process-wide while the context lives) */
 } orc_config;
 
 typedef struct orc_ctx orc_ctx;

@@ -37,7 +37,7 @@ class _Cfg(C.Structure):
         ("newton_max_its", C.c_int),
         ("dt", C.c_double), ("final_time", C.c_double),
         ("ts", C.c_int),
-        ("faithful_ke", C.c_int), ("nthreads", C.c_int),
+        ("faithful_ke", C.c_int), ("nthreads", C.c_int), ("physical_B", C.c_int),
     ]
 
 
@@ -180,6 +180,7 @@ class Config:
     ts: int = 1
     faithful_ke: int = 1
     nthreads: int = 1
+    physical_B: int = 0
     extra: dict = field(default_factory=dict)
 
     def to_c(self) -> _Cfg:

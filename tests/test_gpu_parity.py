@@ -393,3 +393,19 @@ def test_ksp_termination_paths():
     assert its_m == its_o == 7 and m.ksp_reason() == -3
     assert rn_m == pytest.approx(rn_o, rel=1e-9)
     assert rel_err(m.get_vec(M.VEC_DU), o.get_vec("du")) < 1e-10     # same 7 iterates
+
+
+def test_named_switch_physical_B():
+    """SURVEY section 9 quirk switch: B of the physical element instead of the reference's unit
+    cube (assembly.c:198) -- both sides flip together and still agree."""
+    kw = dict(NX=10, NY=5, NZ=6, bc_type=M.BC_BENDING, lx=10., ly=1., lz=2., ts=3)
+    o = O.Oracle(O.Config(physical_B=1, rtol=1e-12, faithful_ke=0, **kw))
+    m = M.MacroC(M.Config(physical_B=1, ksp_rtol=1e-12, **kw))
+    logs = o.run()
+    for t in range(3):
+        assert m.time_step(t)["newton_its"] == logs[t].newton_its
+    assert rel_err(m.get_vec(M.VEC_U), o.get_vec("u")) < TOL_U
+    o.assembly_jac(); m.assembly_jac()
+    assert np.array_equal(m.get_matrix_blocks(), o.block_stencil())
+    ref = O.Oracle(O.Config(rtol=1e-12, faithful_ke=0, **kw)); ref.run()     # the quirk changes the answer
+    assert rel_err(ref.get_vec("u"), o.get_vec("u")) > 1e-3
