@@ -154,7 +154,8 @@ int macroc_calc_force(macroc_ctx *ctx, double *force);     /* forces.c:25-166 */
 
 /* One Newton loop of one time step (main.c:53-82) with the reference's
  * control flow; res_norms gets the |RES| of every iteration (n_res of them),
- * ksp_its the CG iteration count of every solve.  Arrays may be NULL. */
+ * ksp_its the CG iteration count of every solve.  Arrays may be NULL; otherwise
+ * they must hold newton_max_its + 1 entries. */
 int macroc_time_step(macroc_ctx *ctx, int time_s, int *newton_its, double *res_norms,
                      int *n_res, int *ksp_its, double *ksp_rnorms);
 

@@ -336,7 +336,8 @@ class MacroC:
     def time_step(self, time_s: int) -> dict:
         """main.c:53-82 for one time step."""
         nit, nres = C.c_int(), C.c_int()
-        res = (C.c_double * 8)(); kits = (C.c_int * 8)(); krn = (C.c_double * 8)()
+        n = max(int(self.cfg.newton_max_its), 1) + 1           # one |RES| per iteration + the final check
+        res = (C.c_double * n)(); kits = (C.c_int * n)(); krn = (C.c_double * n)()
         self._chk(self._L.macroc_time_step(self._h, time_s, C.byref(nit), res, C.byref(nres), kits, krn))
         return {"newton_its": nit.value, "res_norm": list(res[: nres.value]),
                 "ksp_its": list(kits[: nit.value]), "ksp_rnorm": list(krn[: nit.value])}
