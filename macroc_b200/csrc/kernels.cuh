@@ -433,7 +433,7 @@ k_apply_mf3d(GridDev g, const double *__restrict__ Tg, const uint8_t *__restrict
         }
     }
     if (DOT) {
-        double s = block_sum<8>(dot, sm);
+        double s = block_sum<MF_THREADS / 32>(dot, sm);
         if (threadIdx.x == 0) partial[blockIdx.x] = s;
     }
 }
