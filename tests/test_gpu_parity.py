@@ -29,6 +29,8 @@ GRIDS = [
     (9, 3, 9, M.BC_CIRCLE, dict(lx=4., lz=4.)),        # circle actually loads nodes
     (40, 3, 40, M.BC_CIRCLE, {}),                      # the reference's default grid (macroc.h:44-49)
     (24, 10, 12, M.BC_BENDING, dict(lx=10., ly=1., lz=1.)),
+    (5, 2, 2, M.BC_CIRCLE, {}),                        # tests/CMakeLists.txt:21 as shipped: no node in the
+                                                       # circle, every residual is 0, no solve ever runs
 ]
 
 
@@ -168,11 +170,12 @@ def test_cantilever_config_c2_parity():
 
 
 def test_large_grid_properties():
-    """Size-independent properties at a grid the oracle cannot hold (160^3 nodes,
-    12.3M DOF): symmetry <x, A y> == <y, A x>, rigid translations in the null
-    space of the unconstrained rows, assembled == matrix-free, Dirichlet rows
-    act as identity, linearity."""
-    N = 160
+    """Size-independent properties at BASELINE's full single-GPU size, which the oracle cannot
+    hold (256^3 nodes, 50.3M DOF, 32.7 GB operator): symmetry <x, A y> == <y, A x>, rigid
+    translations in the null space of the unconstrained rows, assembled == matrix-free, Dirichlet
+    rows act as identity, linearity; and the PCG solve of the first Newton step really solves
+    A du = b (checked through the independent matmult hook)."""
+    N = 256
     m = M.MacroC(M.Config(NX=N, NY=N, NZ=N, bc_type=M.BC_BENDING, lx=1., ly=1., lz=1.))
     m.assembly_jac()
     n = m.local_ndof
@@ -189,6 +192,17 @@ def test_large_grid_properties():
     t = np.zeros((N, N, N, 3)); t[..., 1] = 1.0
     At = m.matmult(t.reshape(-1)).reshape(N, N, N, 3)
     assert np.abs(At[:, :, 2:-2, :]).max() < 1e-9 * 8.0e7 * m.cfg.lx / (N - 1)
+    del x3, Ax3, At, t
+    # one Newton step's linear solve at full size: ||b - A du|| is small against ||b||
+    m.apply_bc_on_u(m.get_displacement(1)); m.set_strains()
+    norm_b = m.assembly_res()
+    m.assembly_jac()
+    its, rn = m.solve_Ax()
+    assert 500 < its < 2000 and m.ksp_reason() == 2
+    b = m.get_vec(M.VEC_B); du = m.get_vec(M.VEC_DU)
+    r = b - m.matmult(du)
+    assert np.linalg.norm(r) < 1e-3 * norm_b
+    assert np.isfinite(du).all()
 
 
 @pytest.mark.parametrize("name", ["readme_4x4x2_bending", "ctest_4x4x4_circle", "beam_16x6x6_bending"])
