@@ -238,3 +238,14 @@ def test_openmp_mode_equals_strict_mode():
     assert rel_err(b.block_stencil(), a.block_stencil()) < 1e-14
     assert rel_err(b.get_vec("u"), a.get_vec("u")) < 1e-8
     assert b.time_cg_iterations(2) > 0
+
+
+@pytest.mark.parametrize("grid,bc,extra,its", [((5, 2, 2), 0, {}, 9), ((4, 4, 2), 1, {}, 39), ((4, 4, 4), 1, {}, 28),
+                                              ((16, 6, 6), 0, dict(lx=10.0), 49)])
+def test_cg_iteration_counts_of_the_survey(grid, bc, extra, its):
+    """CG iteration counts of the first loaded time step, obtained there with an
+    independent numpy restatement of PETSc's KSPCG + PCJACOBI semantics."""
+    NX, NY, NZ = grid
+    o = O.Oracle(O.Config(NX=NX, NY=NY, NZ=NZ, bc_type=bc, ts=2, **extra))
+    logs = o.run()
+    assert logs[0].newton_its == 0 and logs[1].newton_its == 1 and logs[1].ksp_its == [its]
