@@ -162,3 +162,32 @@ def test_config_struct_layout_matches_ctypes_mirror(tmp_path):
     assert int(out["sizeof"]) == C.sizeof(capi.CConfig)
     for f in fields:
         assert int(out[f]) == getattr(capi.CConfig, f).offset, f
+
+
+def test_partition_and_bc_lists_fuzz():
+    """Random grids and processor grids (hypothesis): the library's DMDA restatement and Dirichlet
+    lists equal the oracle's for every rank, or both refuse the decomposition."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.integers(2, 11), st.integers(2, 9), st.integers(2, 11), st.integers(1, 8),
+           st.sampled_from([0, 1, 2, 3]), st.sampled_from([0, 1, 2]), st.sampled_from([0, 1, 2, 4]),
+           st.sampled_from([M.BC_BENDING, M.BC_CIRCLE]))
+    def check(NX, NY, NZ, nranks, px, py, pz, bc):
+        kw = dict(NX=NX, NY=NY, NZ=NZ, bc_type=bc, lx=4.0, lz=5.0, px=px, py=py, pz=pz)
+        try:
+            o = O.Oracle(O.Config(nranks=nranks, **kw))
+        except ValueError:
+            o = None
+        if o is None or any(v <= 0 for v in o.proc_grid):
+            with pytest.raises(M.MacrocError):
+                M.partition(M.Config(**kw), 0, nranks)
+            return
+        for r in range(nranks):
+            p = M.partition(M.Config(**kw), r, nranks)
+            assert p["corners"] == o.corners(r) and p["ghost_corners"] == o.ghost_corners(r)
+            assert p["elements_sizes"] == o.elements_sizes(r)
+            idx, _ = M.bc_lists(M.Config(**kw), r, nranks)
+            assert np.array_equal(idx, o.bc_list(r))
+
+    check()
