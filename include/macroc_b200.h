@@ -39,7 +39,9 @@ extern "C" {
 
 enum { MACROC_BC_BENDING = 0, MACROC_BC_CIRCLE = 1 };          /* include/macroc.h:58 */
 enum { MACROC_VEC_U = 0, MACROC_VEC_DU = 1, MACROC_VEC_B = 2 }; /* include/macroc.h:128 */
-enum { MACROC_OP_ASSEMBLED = 0, MACROC_OP_MATRIX_FREE = 1 };
+enum { MACROC_OP_ASSEMBLED = 0, MACROC_OP_MATRIX_FREE = 1,
+       MACROC_OP_ASSEMBLED_SYM = 2 };  /* assembled, symmetric storage: 14 of the 27 slots
+                                          (opt-in; uniform tangent, one rank in this round) */
 /* where the Gauss-point stress / tangent come from (the MicroPP boundary) */
 enum { MACROC_MAT_UNIFORM = 0,   /* sigma = D eps, C = D in registers (north_star's fixed D)    */
        MACROC_MAT_PER_GP = 1 };  /* device arrays strain/stress[ngp*6], ctan[ngp*36], gpi=ie*8+gp */
@@ -184,7 +186,8 @@ int macroc_write_pvtu(macroc_ctx *ctx, const char *file_prefix);
  * already resident in HBM and returns the mean device time per launch in ms
  * (CUDA events on that stream).  what: 0 SpMV assembled, 1 apply matrix-free,
  * 2 one full PCG iteration (assembled), 3 Jacobian assembly, 4 residual,
- * 5 one full PCG iteration (matrix-free), 7 per-element Jacobian kernel.
+ * 5 one full PCG iteration (matrix-free), 7 per-element Jacobian kernel,
+ * 8 SpMV with symmetric storage, 9 one full PCG iteration with it.
  * flush_l2 != 0 writes a >L2 buffer between launches.  Clobbers b, du and the
  * KSP work vectors (2, 5) -- a measurement hook, not part of the solve path. */
 int macroc_time_kernel(macroc_ctx *ctx, int what, int reps, int flush_l2, double *ms_mean);

@@ -20,7 +20,7 @@ CSRC = os.path.join(HERE, "csrc")
 
 BC_BENDING, BC_CIRCLE = 0, 1
 VEC_U, VEC_DU, VEC_B = 0, 1, 2
-OP_ASSEMBLED, OP_MATRIX_FREE = 0, 1
+OP_ASSEMBLED, OP_MATRIX_FREE, OP_ASSEMBLED_SYM = 0, 1, 2
 MAT_UNIFORM, MAT_PER_GP = 0, 1
 JAC_AUTO, JAC_ELEMENT = 0, 1
 ERR_NO_DEVICE = 97

@@ -22,6 +22,7 @@
 #include "kernels.cuh"
 #include "spmv_tma.cuh"
 #include "assembly_elem.cuh"
+#include "spmv_sym.cuh"
 
 using namespace macroc;
 
@@ -40,7 +41,8 @@ struct macroc_ctx {
     ncclComm_t comm = nullptr;
     double *vec[V_COUNT] = {nullptr};
     double2 *A = nullptr;
-    bool A_valid = false, mf_ready = false;
+    double2 *Asym = nullptr;         // symmetric storage (14 of 27 slots), MACROC_OP_ASSEMBLED_SYM
+    bool A_valid = false, mf_ready = false, Asym_valid = false;
     double *Ke = nullptr, *T = nullptr;
     uint8_t *nodemask = nullptr, *ghostflag = nullptr;
     double *xy_halo = nullptr;       // 4 send + 4 receive staging buffers of the x / y halo
@@ -68,8 +70,8 @@ struct macroc_ctx {
     uint64_t launches = 0;
     int ksp_reason = 0;
     int vec_blocks = 0, spmv_blocks = 0;
-    cudaGraphExec_t cg_graph[2] = {nullptr, nullptr};   // `check` PCG iterations per launch, per operator
-    uint64_t cg_graph_launches[2] = {0, 0};
+    cudaGraphExec_t cg_graph[3] = {nullptr, nullptr, nullptr};   // `check` PCG iterations per launch, per operator
+    uint64_t cg_graph_launches[3] = {0, 0, 0};
     int spmv_variant = 10;           // 10: TMA ring 8 warps x 4 stages (default); 11: 8x5, 14: 6x6; 0: per-lane LDG
                                      // (kept for A/B measurements, tools/spmv_sweep.py; MACROC_SPMV_VARIANT)
     cudaEvent_t ev_user[8] = {nullptr};
@@ -265,7 +267,7 @@ static int ctx_free(macroc_ctx *c)
     if (c->comm) ncclCommDestroy(c->comm);
     for (cudaGraphExec_t ge : c->cg_graph) if (ge) cudaGraphExecDestroy(ge);
     for (int i = 0; i < V_COUNT; ++i) cudaFree(c->vec[i]);
-    cudaFree(c->A); cudaFree(c->Ke); cudaFree(c->T); cudaFree(c->nodemask); cudaFree(c->bc_idx); cudaFree(c->bc_coef);
+    cudaFree(c->A); cudaFree(c->Asym); cudaFree(c->Ke); cudaFree(c->T); cudaFree(c->nodemask); cudaFree(c->bc_idx); cudaFree(c->bc_coef);
     cudaFree(c->partial); cudaFree(c->sums); cudaFree(c->sc); cudaFree(c->stage); cudaFree(c->strain); cudaFree(c->stress);
     cudaFree(c->ctan); cudaFree(c->scratch); cudaFree(c->consts); cudaFree(c->gp_halo); cudaFree(c->ghostflag); cudaFree(c->xy_halo);
     if (c->device >= 0 && c->device < 64 && g_const_owner[c->device] == c->id) g_const_owner[c->device] = 0;
@@ -733,7 +735,17 @@ extern "C" int macroc_assembly_jac(macroc_ctx *c)
     if (!c) return MACROC_ERR_ARG;
     CU(c, cudaSetDevice(c->device));
     { int _rc = bind_constants(c); if (_rc) return _rc; }
-    if (c->cfg.op == MACROC_OP_MATRIX_FREE) {
+    if (c->cfg.op == MACROC_OP_ASSEMBLED_SYM) {
+        if (c->cfg.material != MACROC_MAT_UNIFORM || c->comm)
+            FAIL(c, MACROC_ERR_UNSUPPORTED, "symmetric operator storage: uniform tangent on one rank only (this round)");
+        if (!c->Asym) {
+            size_t bytes = (size_t)SYM_TILE_BYTES * (size_t)c->g.ntiles;
+            cudaError_t e = cudaMalloc(&c->Asym, bytes);
+            if (e != cudaSuccess) { cudaGetLastError(); FAIL(c, MACROC_ERR_MEM, "operator needs %.2f GB of device memory", bytes / 1e9); }
+        }
+        LAUNCH(c, k_fill_operator_sym, cdiv64(c->g.ntiles, 8), 256, c->g, c->T, c->nodemask, c->Asym, c->vec[V_DINV]);
+        c->Asym_valid = true;
+    } else if (c->cfg.op == MACROC_OP_MATRIX_FREE) {
         if (c->cfg.material != MACROC_MAT_UNIFORM) FAIL(c, MACROC_ERR_UNSUPPORTED, "matrix-free operator needs the uniform tangent");
         LAUNCH(c, k_mf_diag, cdiv64(c->g.nloc, 256), 256, c->g, c->T, c->nodemask, c->vec[V_DINV]);
         c->mf_ready = true;
@@ -836,7 +848,25 @@ static int apply_operator(macroc_ctx *c, int op, double *p, double *w, bool with
     auto run = [&](int64_t first, int64_t count) {
         if (count <= 0) return;
         int blocks;
-        if (mf) {
+        if (op == MACROC_OP_ASSEMBLED_SYM) {
+            constexpr int W = 8, NS = 4;
+            const int smem = W * NS * CHUNK_BYTES + W * NS * 8 + W * 8;
+            static bool configured[64] = {false};
+            if (!configured[c->device & 63]) {
+                cudaFuncSetAttribute(k_spmv_sym<W, NS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+                cudaFuncSetAttribute(k_spmv_sym<W, NS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+                configured[c->device & 63] = true;
+            }
+            const int64_t tpp = (g.npl + TILE_NODES - 1) / TILE_NODES, rt = (g.NX + TILE_NODES - 1) / TILE_NODES;
+            const int64_t pencils = rt * ((((tpp + rt - 1) / rt) + W - 1) / W);
+            int nseg = (int)std::max<int64_t>(1, (148 * 7 + pencils - 1) / pencils);
+            const int64_t mtot = (g.ntiles + tpp - 1) / tpp;
+            nseg = (int)std::min<int64_t>(nseg, std::max<int64_t>(1, mtot / 8));     // segments of >= 8 planes
+            blocks = (int)std::min<int64_t>(pencils * nseg, 148);
+            if (with_dot) k_spmv_sym<W, NS, true><<<blocks, W * 32, smem, c->stream>>>(g, c->Asym, p, w, first, count, tpp, rt, nseg, c->partial + nparts, done);
+            else k_spmv_sym<W, NS, false><<<blocks, W * 32, smem, c->stream>>>(g, c->Asym, p, w, first, count, tpp, rt, nseg, c->partial + nparts, done);
+            c->launches++;
+        } else if (mf) {
             // node ranges are whole planes here
             const int k0 = (int)(first / g.npl), k1 = (int)((first + count) / g.npl);
             const int tiles_x = (g.NX + MF_TX - 1) / MF_TX, tiles_y = (g.NY + MF_TY - 1) / MF_TY;
@@ -926,6 +956,7 @@ extern "C" int macroc_solve_Ax(macroc_ctx *c, int *its, double *rnorm)
     { int _rc = bind_constants(c); if (_rc) return _rc; }
     const int op = c->cfg.op;
     if (op == MACROC_OP_ASSEMBLED && !c->A_valid) FAIL(c, MACROC_ERR_ARG, "solve_Ax: assembly_jac has not been called");
+    if (op == MACROC_OP_ASSEMBLED_SYM && !c->Asym_valid) FAIL(c, MACROC_ERR_ARG, "solve_Ax: assembly_jac has not been called");
     if (op == MACROC_OP_MATRIX_FREE && !c->mf_ready) FAIL(c, MACROC_ERR_ARG, "solve_Ax: assembly_jac has not been called");
     int rc = cg_begin(c, c->cfg.ksp_rtol, c->cfg.ksp_abstol, c->cfg.ksp_dtol, c->cfg.ksp_maxits);
     if (rc) return rc;
@@ -993,7 +1024,9 @@ extern "C" int macroc_solve_Ax(macroc_ctx *c, int *its, double *rnorm)
 
 extern "C" int macroc_set_operator(macroc_ctx *c, int op)
 {
-    if (!c || (op != MACROC_OP_ASSEMBLED && op != MACROC_OP_MATRIX_FREE)) return MACROC_ERR_ARG;
+    if (!c || (op != MACROC_OP_ASSEMBLED && op != MACROC_OP_MATRIX_FREE && op != MACROC_OP_ASSEMBLED_SYM)) return MACROC_ERR_ARG;
+    if (op == MACROC_OP_ASSEMBLED_SYM && (c->cfg.material != MACROC_MAT_UNIFORM || c->comm))
+        FAIL(c, MACROC_ERR_UNSUPPORTED, "symmetric operator storage: uniform tangent on one rank only (this round)");
     if (op == MACROC_OP_MATRIX_FREE && c->cfg.material != MACROC_MAT_UNIFORM)
         FAIL(c, MACROC_ERR_UNSUPPORTED, "matrix-free operator needs the uniform tangent");
     c->cfg.op = op;
@@ -1124,7 +1157,8 @@ extern "C" int macroc_get_vec(macroc_ctx *c, int which, double *host)
 extern "C" int macroc_get_matrix_blocks(macroc_ctx *c, double *host)
 {
     if (!c || !host) return MACROC_ERR_ARG;
-    if (!c->A_valid) FAIL(c, MACROC_ERR_ARG, "get_matrix_blocks: no assembled operator");
+    const bool sym = c->cfg.op == MACROC_OP_ASSEMBLED_SYM;
+    if (sym ? !c->Asym_valid : !c->A_valid) FAIL(c, MACROC_ERR_ARG, "get_matrix_blocks: no assembled operator");
     CU(c, cudaSetDevice(c->device));
     const int64_t chunk = 1 << 16;                 // nodes per export chunk
     double *tmp = nullptr;
@@ -1132,7 +1166,8 @@ extern "C" int macroc_get_matrix_blocks(macroc_ctx *c, double *host)
     const int64_t nown = (int64_t)c->g.xm * c->g.ym * c->g.nzl;
     for (int64_t n0 = 0; n0 < nown; n0 += chunk) {
         int64_t nn = std::min<int64_t>(chunk, nown - n0);
-        LAUNCH(c, k_export_blocks, cdiv64(nn * 243, 256), 256, c->g, reinterpret_cast<const double *>(c->A), n0, nn, tmp);
+        if (sym) LAUNCH(c, k_export_blocks_sym, cdiv64(nn * 243, 256), 256, c->g, reinterpret_cast<const double *>(c->Asym), n0, nn, tmp);
+        else LAUNCH(c, k_export_blocks, cdiv64(nn * 243, 256), 256, c->g, reinterpret_cast<const double *>(c->A), n0, nn, tmp);
         cudaError_t e = cudaMemcpyAsync(host + n0 * 243, tmp, sizeof(double) * 243 * nn, cudaMemcpyDeviceToHost, c->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
         if (e != cudaSuccess) { cudaFree(tmp); FAIL(c, MACROC_ERR_CUDA, "get_matrix_blocks: %s", cudaGetErrorString(e)); }
@@ -1147,6 +1182,7 @@ extern "C" int macroc_matmult(macroc_ctx *c, int op, const double *x_host, doubl
     CU(c, cudaSetDevice(c->device));
     { int _rc = bind_constants(c); if (_rc) return _rc; }
     if (op == MACROC_OP_ASSEMBLED && !c->A_valid) FAIL(c, MACROC_ERR_ARG, "matmult: no assembled operator");
+    if (op == MACROC_OP_ASSEMBLED_SYM && !c->Asym_valid) FAIL(c, MACROC_ERR_ARG, "matmult: no symmetric operator");
     int64_t n = macroc_local_ndof(c);
     CU(c, cudaMemcpyAsync(c->stage, x_host, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
     LAUNCH(c, k_aos_to_soa, cdiv64(n, 256), 256, c->g, c->stage, c->vec[V_P]);
@@ -1356,12 +1392,13 @@ extern "C" int macroc_time_kernel(macroc_ctx *c, int what, int reps, int flush_l
     { int _rc = bind_constants(c); if (_rc) return _rc; }
     const GridDev &g = c->g;
     if ((what == 0 || what == 2) && !c->A_valid) FAIL(c, MACROC_ERR_ARG, "time_kernel: assemble first");
+    if ((what == 8 || what == 9) && !c->Asym_valid) FAIL(c, MACROC_ERR_ARG, "time_kernel: assemble the symmetric operator first");
     if (flush_l2 && !c->flush) {
         c->flush_bytes = (size_t)256 << 20;
         CU(c, cudaMalloc(&c->flush, c->flush_bytes));
     }
-    if (what == 0 || what == 1) LAUNCH(c, k_fill_pattern, cdiv64(g.nloc, 256), 256, g, c->nodemask, c->vec[V_P]);
-    if (what == 2 || what == 5) {
+    if (what == 0 || what == 1 || what == 8) LAUNCH(c, k_fill_pattern, cdiv64(g.nloc, 256), 256, g, c->nodemask, c->vec[V_P]);
+    if (what == 2 || what == 5 || what == 9) {
         // a never-converging PCG on a synthetic right-hand side: every iteration does the full work
         if (what == 5) LAUNCH(c, k_mf_diag, cdiv64(g.nloc, 256), 256, g, c->T, c->nodemask, c->vec[V_DINV]);
         LAUNCH(c, k_fill_pattern, cdiv64(g.nloc, 256), 256, g, c->nodemask, c->vec[V_B]);
@@ -1378,6 +1415,8 @@ extern "C" int macroc_time_kernel(macroc_ctx *c, int what, int reps, int flush_l
             case 1: rc = apply_operator(c, MACROC_OP_MATRIX_FREE, c->vec[V_P], c->vec[V_W], true, nullptr); break;
             case 2: rc = cg_iteration(c, MACROC_OP_ASSEMBLED); break;
             case 5: rc = cg_iteration(c, MACROC_OP_MATRIX_FREE); break;
+            case 8: rc = apply_operator(c, MACROC_OP_ASSEMBLED_SYM, c->vec[V_P], c->vec[V_W], true, nullptr); break;
+            case 9: rc = cg_iteration(c, MACROC_OP_ASSEMBLED_SYM); break;
             case 3: {
                 int save = c->cfg.op; c->cfg.op = MACROC_OP_ASSEMBLED;
                 rc = macroc_assembly_jac(c);

@@ -1,0 +1,235 @@
+// spmv_sym.cuh -- symmetric storage of the assembled operator (opt-in, MACROC_OP_ASSEMBLED_SYM).
+//
+// A = M K M + I - M is symmetric, so block (i, s) equals the transpose of block (i + off_s, 26 - s).
+// Only the 14 slots s = 13..26 (the diagonal block and the 13 neighbours at a non-negative
+// linear offset) are stored: 126 entries = 63 double2 pairs per node, 1 008 B/node instead of
+// 1 952.  Same tile idea as the full layout: 32 consecutive local nodes, entry
+// k' = (s-13)*9 + 3r + c of node `lane` at double index ((k'>>1)*32 + lane)*2 + (k'&1) of its
+// 32 256-byte tile; a tile is 7 TMA chunks of two slots each.
+//
+// SpMV in GATHER form (no atomics, no colouring, bit-reproducible):
+//     w_i = sum_{s=13..26} A[i][s] p_{i+off_s}  +  sum_{s=14..26} A[i-off_s][s]^T p_{i-off_s}
+// The first sum streams the node's own tile through the TMA ring (read from HBM once); the
+// second reads the 13 lower neighbours' blocks with plain loads.  Those blocks were streamed
+// moments earlier by the same CTA when the traversal keeps z- and y-neighbours close, so they
+// hit L2: a CTA owns a "pencil" (one x-tile, 8 consecutive rows, one warp per row) and sweeps
+// it upward in z.  The traversal only affects locality, never the result.
+#pragma once
+
+#include "kernels.cuh"
+#include "spmv_tma.cuh"
+
+namespace macroc {
+
+constexpr int SYM_ENTRIES = 126;                       // 14 slots x 9
+constexpr int SYM_PAIRS = 63;
+constexpr int SYM_TILE_DOUBLES = SYM_PAIRS * 2 * TILE_NODES;      // 4032 doubles = 32 256 B
+constexpr int SYM_TILE_BYTES = SYM_TILE_DOUBLES * 8;
+constexpr int SYM_CHUNKS = 7;                          // 7 x 9 pairs = 63
+
+__device__ __forceinline__ double sym_entry(const double *__restrict__ A, int64_t node, int kp)
+{
+    const int64_t tile = node >> 5;
+    const int lane = (int)(node & 31);
+    return __ldg(A + tile * SYM_TILE_DOUBLES + ((int64_t)(kp >> 1) * TILE_NODES + lane) * 2 + (kp & 1));
+}
+
+// Jacobian "assembly" for a uniform tangent into the symmetric layout (cf. k_fill_operator).
+__global__ void __launch_bounds__(256)
+k_fill_operator_sym(GridDev g, const double *__restrict__ T, const uint8_t *__restrict__ nodemask,
+                    double2 *__restrict__ A, double *__restrict__ dinv)
+{
+    int64_t tile = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (tile >= g.ntiles) return;
+    int lane = threadIdx.x & 31;
+    int64_t ln = tile * TILE_NODES + lane;
+    bool valid = ln < g.nloc;
+    int type = 13;
+    unsigned own = 0;
+    if (valid) {
+        int i = (int)(ln % g.NX), j = (int)((ln / g.NX) % g.NY), k = (int)(ln / g.npl) + g.zs;
+        type = node_class(i, g.NX) + 3 * node_class(j, g.NY) + 9 * node_class(k, g.NZ);
+        own = nodemask[g.G + ln];
+    }
+    const double *Tt = T + type * 243;
+    double2 *At = A + tile * (SYM_PAIRS * TILE_NODES) + lane;
+    double carry = 0.;
+    double diag[3] = {1., 1., 1.};
+#pragma unroll
+    for (int kp = 0; kp < SYM_ENTRIES; ++kp) {
+        const int slot = 13 + kp / 9, rr = (kp % 9) / 3, cc = kp % 3;
+        const int ddx = slot % 3 - 1, ddy = (slot / 3) % 3 - 1, ddz = slot / 9 - 1;
+        double v = 0.;
+        if (valid) {
+            v = __ldg(Tt + slot * 9 + 3 * rr + cc);
+            unsigned nb = nodemask[g.G + ln + ddx + (int64_t)g.NX * ddy + g.npl * ddz];
+            if (((own >> rr) & 1u) || ((nb >> cc) & 1u)) v = (slot == 13 && rr == cc) ? 1. : 0.;
+            if (slot == 13 && rr == cc) diag[rr] = v;
+        }
+        if (kp & 1) At[(kp >> 1) * TILE_NODES] = make_double2(carry, v);
+        else carry = v;
+    }
+    if (valid) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) dinv[d * g.S + g.G + ln] = diag[d] != 0. ? 1. / diag[d] : 1.;
+    }
+}
+
+// full 27-slot view of owned nodes from the symmetric storage (export / tests)
+__global__ void k_export_blocks_sym(GridDev g, const double *__restrict__ A, int64_t node0, int64_t nnodes,
+                                    double *__restrict__ out /* [nnodes][243] */)
+{
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nnodes * 243) return;
+    const int64_t ln = owned_to_local(g, node0 + e / 243);
+    const int kk = (int)(e % 243), slot = kk / 9, rr = (kk % 9) / 3, cc = kk % 3;
+    double v;
+    if (slot >= 13) v = sym_entry(A, ln, (slot - 13) * 9 + 3 * rr + cc);
+    else {
+        // block (i, s) = transpose of block (i + off_s, 26 - s), stored with node i + off_s
+        const int ddx = slot % 3 - 1, ddy = (slot / 3) % 3 - 1, ddz = slot / 9 - 1;
+        const int64_t j = ln + ddx + (int64_t)g.NX * ddy + g.npl * ddz;
+        v = j >= 0 ? sym_entry(A, j, (26 - slot - 13) * 9 + 3 * cc + rr) : 0.;
+    }
+    out[e] = v;
+}
+
+template <int WARPS, int NSTAGE, bool DOT>
+__global__ void __launch_bounds__(WARPS * 32, 1)
+k_spmv_sym(GridDev g, const double2 *__restrict__ A, const double *__restrict__ p, double *__restrict__ w,
+           int64_t tile0, int64_t ntiles_range, int64_t tpp /* tiles per plane (rounded up) */,
+           int64_t rt /* tiles per x-row (rounded up) */, int nseg, double *__restrict__ partial,
+           const int *__restrict__ done)
+{
+    static_assert(NSTAGE >= 2 && NSTAGE <= SYM_CHUNKS, "ring depth");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    if (done && *done) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned char *ring = smem_raw + (size_t)warp * NSTAGE * CHUNK_BYTES;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + (size_t)WARPS * NSTAGE * CHUNK_BYTES) + warp * NSTAGE;
+    double *red = reinterpret_cast<double *>(smem_raw + (size_t)WARPS * NSTAGE * CHUNK_BYTES + (size_t)WARPS * NSTAGE * 8);
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < NSTAGE; ++s) mbar_init(&bars[s], 1);
+        fence_barrier_init();
+    }
+    __syncwarp();
+    const unsigned char *Ab = reinterpret_cast<const unsigned char *>(A);
+    const double *Ad = reinterpret_cast<const double *>(A);
+    const uint64_t policy = l2_evict_first_policy();     // unused lines leave L2 first; see the plain loads below
+    (void)policy;
+    const int64_t NX = g.NX, npl = g.npl;
+    const int64_t tile_end = tile0 + ntiles_range;
+    // work items: pencil (x-tile xt, block of WARPS rows yb) x z-segment; column of warp = xt + rt*(yb*WARPS + warp)
+    const int64_t rows = (tpp + rt - 1) / rt, yblocks = (rows + WARPS - 1) / WARPS;
+    const int64_t mtot = (g.ntiles + tpp - 1) / tpp;                  // tiles per column (planes)
+    const int64_t mseg = (mtot + nseg - 1) / nseg;
+    const int64_t items = rt * yblocks * nseg;
+    double dot = 0.;
+    int64_t c = 0;                                                   // chunk counter of this warp (ring phase)
+    for (int64_t item = blockIdx.x; item < items; item += gridDim.x) {
+        const int64_t seg = item / (rt * yblocks), pen = item % (rt * yblocks);
+        const int64_t xt = pen % rt, yb = pen / rt;
+        const int64_t col = xt + rt * (yb * WARPS + warp);
+        if (col >= tpp) continue;                                    // warp-uniform
+        const int64_t m0 = seg * mseg, m1 = min(mtot, m0 + mseg);
+        // this warp's tile sequence: col + m*tpp, m in [m0, m1), clipped to [tile0, tile_end)
+        int64_t first = -1, count = 0;
+        for (int64_t m = m0; m < m1; ++m) {
+            const int64_t t = col + m * tpp;
+            if (t >= tile0 && t < tile_end) { if (first < 0) first = m; count++; }
+        }
+        if (count == 0) continue;
+        const int64_t nch = count * SYM_CHUNKS;
+        const int64_t c0 = c;                                        // ring position at the start of the item
+        auto issue = [&](int64_t qi) {                               // qi-th chunk of this item's sequence
+            const int64_t tq = col + (first + qi / SYM_CHUNKS) * tpp;
+            const int ch = (int)(qi % SYM_CHUNKS);
+            const int stage = (int)((c0 + qi) % NSTAGE);
+            mbar_arrive_expect_tx(&bars[stage], CHUNK_BYTES);
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(smem_u32(ring + stage * CHUNK_BYTES)),
+                           "l"(Ab + tq * (int64_t)SYM_TILE_BYTES + (int64_t)ch * CHUNK_BYTES), "r"((uint32_t)CHUNK_BYTES),
+                           "r"(smem_u32(&bars[stage])) : "memory");
+        };
+        if (lane == 0)
+            for (int64_t qi = 0; qi < NSTAGE && qi < nch; ++qi) issue(qi);
+        int64_t q = 0;
+        for (int64_t mm = 0; mm < count; ++mm) {
+            const int64_t tile = col + (first + mm) * tpp;
+            const int64_t ln = tile * TILE_NODES + lane;
+            const double *p0 = p + g.G + ln, *p1 = p0 + g.S, *p2 = p1 + g.S;
+            double a0 = 0., a1 = 0., a2 = 0., pc0 = 0., pc1 = 0., pc2 = 0.;
+            // (1) transposed blocks of the 13 lower neighbours: plain loads, expected to hit L2
+#pragma unroll
+            for (int s = 14; s < 27; ++s) {
+                const int ddx = s % 3 - 1, ddy = (s / 3) % 3 - 1, ddz = s / 9 - 1;
+                const int64_t off = ddx + NX * ddy + npl * ddz;
+                const int64_t j = ln - off;
+                const double x0 = __ldg(p0 - off), x1 = __ldg(p1 - off), x2 = __ldg(p2 - off);
+                if (j >= 0 && j < g.ntiles * TILE_NODES) {
+                    const double *bj = Ad + (j >> 5) * SYM_TILE_DOUBLES + (j & 31) * 2;
+                    double m[9];
+#pragma unroll
+                    for (int e = 0; e < 9; ++e) {
+                        const int kp = (s - 13) * 9 + e;
+                        m[e] = __ldg(bj + (kp >> 1) * (TILE_NODES * 2) + (kp & 1));
+                    }
+                    // w_i[c] += sum_r A[j][s][r][c] * p_j[r]
+                    a0 = fma(m[0], x0, a0); a0 = fma(m[3], x1, a0); a0 = fma(m[6], x2, a0);
+                    a1 = fma(m[1], x0, a1); a1 = fma(m[4], x1, a1); a1 = fma(m[7], x2, a1);
+                    a2 = fma(m[2], x0, a2); a2 = fma(m[5], x1, a2); a2 = fma(m[8], x2, a2);
+                }
+            }
+            // (2) own upper blocks (slots 13..26) from the TMA ring
+#pragma unroll
+            for (int ch = 0; ch < SYM_CHUNKS; ++ch, ++q, ++c) {
+                const int stage = (int)(c % NSTAGE);
+                const uint32_t parity = (uint32_t)((c / NSTAGE) & 1);
+                double xv[2][3];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int slot = 13 + 2 * ch + h;
+                    const int ddx = slot % 3 - 1, ddy = (slot / 3) % 3 - 1, ddz = slot / 9 - 1;
+                    const int64_t off = ddx + NX * ddy + npl * ddz;
+                    xv[h][0] = __ldg(p0 + off); xv[h][1] = __ldg(p1 + off); xv[h][2] = __ldg(p2 + off);
+                    if (slot == 13) { pc0 = xv[h][0]; pc1 = xv[h][1]; pc2 = xv[h][2]; }
+                }
+                mbar_wait(&bars[stage], parity);
+                const double2 *sv = reinterpret_cast<const double2 *>(ring + stage * CHUNK_BYTES) + lane;
+                double2 v[9];
+#pragma unroll
+                for (int e = 0; e < 9; ++e) v[e] = sv[e * TILE_NODES];
+                const double *ev = reinterpret_cast<const double *>(v);
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const double *m = ev + 9 * h;
+                    const double x0 = xv[h][0], x1 = xv[h][1], x2 = xv[h][2];
+                    a0 = fma(m[0], x0, a0); a0 = fma(m[1], x1, a0); a0 = fma(m[2], x2, a0);
+                    a1 = fma(m[3], x0, a1); a1 = fma(m[4], x1, a1); a1 = fma(m[5], x2, a1);
+                    a2 = fma(m[6], x0, a2); a2 = fma(m[7], x1, a2); a2 = fma(m[8], x2, a2);
+                }
+                __syncwarp();
+                if (lane == 0 && q + NSTAGE < nch) issue(q + NSTAGE);
+            }
+            if (ln < g.nloc) {
+                double *w0 = w + g.G + ln;
+                w0[0] = a0; w0[g.S] = a1; w0[2 * g.S] = a2;
+                if (DOT && owned_node(g, ln)) dot += a0 * pc0 + a1 * pc1 + a2 * pc2;
+            }
+        }
+    }
+    if (DOT) {
+        dot = warp_sum(dot);
+        if (lane == 0) red[warp] = dot;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double s = 0.;
+#pragma unroll
+            for (int qq = 0; qq < WARPS; ++qq) s += red[qq];
+            partial[blockIdx.x] = s;
+        }
+    }
+}
+
+}  // namespace macroc

@@ -423,3 +423,23 @@ def test_named_switch_physical_B():
     assert np.array_equal(m.get_matrix_blocks(), o.block_stencil())
     ref = O.Oracle(O.Config(rtol=1e-12, faithful_ke=0, **kw)); ref.run()     # the quirk changes the answer
     assert rel_err(ref.get_vec("u"), o.get_vec("u")) > 1e-3
+
+
+@pytest.mark.parametrize("NX,NY,NZ,bc,extra", [GRIDS[0], GRIDS[4], GRIDS[6], GRIDS[7], GRIDS[8], GRIDS[9], GRIDS[10],
+                                              (64, 40, 21, M.BC_BENDING, dict(lx=10., ly=1., lz=1.)),
+                                              (70, 9, 12, M.BC_CIRCLE, dict(lx=4., lz=4.))])
+def test_symmetric_storage_operator(NX, NY, NZ, bc, extra):
+    """MACROC_OP_ASSEMBLED_SYM stores 14 of the 27 slots; its full view, its SpMV and the solve
+    must equal the full-storage operator / the oracle."""
+    o = O.Oracle(O.Config(NX=NX, NY=NY, NZ=NZ, bc_type=bc, ts=3, rtol=1e-12, faithful_ke=0, **extra))
+    m = M.MacroC(M.Config(NX=NX, NY=NY, NZ=NZ, bc_type=bc, ts=3, ksp_rtol=1e-12, op=M.OP_ASSEMBLED_SYM, **extra))
+    o.assembly_jac(); m.assembly_jac()
+    assert np.array_equal(m.get_matrix_blocks(), o.block_stencil())        # reconstructed full view, bitwise
+    x = np.random.default_rng(13).standard_normal(o.ndof)
+    assert rel_err(m.matmult(x, M.OP_ASSEMBLED_SYM), o.matmult(x)) < 1e-13
+    logs = o.run()
+    for t in range(3):
+        r = m.time_step(t)
+        assert r["newton_its"] == logs[t].newton_its
+        assert all(abs(a - b) <= 2 for a, b in zip(r["ksp_its"], logs[t].ksp_its))
+    assert rel_err(m.get_vec(M.VEC_U), o.get_vec("u")) < TOL_U
