@@ -94,12 +94,28 @@ __global__ void k_export_blocks_sym(GridDev g, const double *__restrict__ A, int
     out[e] = v;
 }
 
-template <int WARPS, int NSTAGE, bool DOT>
-__global__ void __launch_bounds__(WARPS * 32, 1)
+// L2 eviction-priority policies: 0 normal, 1 evict_first, 2 evict_last
+__device__ __forceinline__ uint64_t l2_policy(int kind)
+{
+    uint64_t pol;
+    if (kind == 1) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    else if (kind == 2) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ double2 ldg_hint(const double2 *ptr, uint64_t pol)
+{
+    double2 v;
+    asm("ld.global.nc.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(ptr), "l"(pol));
+    return v;
+}
+
+template <int WARPS, int NSTAGE, int MINB, bool DOT>
+__global__ void __launch_bounds__(WARPS * 32, MINB)
 k_spmv_sym(GridDev g, const double2 *__restrict__ A, const double *__restrict__ p, double *__restrict__ w,
            int64_t tile0, int64_t ntiles_range, int64_t tpp /* tiles per plane (rounded up) */,
            int64_t rt /* tiles per x-row (rounded up) */, int nseg, double *__restrict__ partial,
-           const int *__restrict__ done)
+           const int *__restrict__ done, int hint /* L2 policy: stream = hint / 4, second use = hint % 4 */)
 {
     static_assert(NSTAGE >= 2 && NSTAGE <= SYM_CHUNKS, "ring depth");
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -116,8 +132,9 @@ k_spmv_sym(GridDev g, const double2 *__restrict__ A, const double *__restrict__ 
     __syncwarp();
     const unsigned char *Ab = reinterpret_cast<const unsigned char *>(A);
     const double *Ad = reinterpret_cast<const double *>(A);
-    const uint64_t policy = l2_evict_first_policy();     // unused lines leave L2 first; see the plain loads below
-    (void)policy;
+    // every block is used twice: streamed by the TMA engine with its own tile, then read once
+    // more as the transposed block of a neighbour.  After the second use the line is dead.
+    const uint64_t pol_stream = l2_policy(hint >> 2), pol_again = l2_policy(hint & 3);
     const int64_t NX = g.NX, npl = g.npl;
     const int64_t tile_end = tile0 + ntiles_range;
     // work items: pencil (x-tile xt, block of WARPS rows yb) x z-segment; column of warp = xt + rt*(yb*WARPS + warp)
@@ -147,10 +164,8 @@ k_spmv_sym(GridDev g, const double2 *__restrict__ A, const double *__restrict__ 
             const int ch = (int)(qi % SYM_CHUNKS);
             const int stage = (int)((c0 + qi) % NSTAGE);
             mbar_arrive_expect_tx(&bars[stage], CHUNK_BYTES);
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         ::"r"(smem_u32(ring + stage * CHUNK_BYTES)),
-                           "l"(Ab + tq * (int64_t)SYM_TILE_BYTES + (int64_t)ch * CHUNK_BYTES), "r"((uint32_t)CHUNK_BYTES),
-                           "r"(smem_u32(&bars[stage])) : "memory");
+            tma_load_bulk(ring + stage * CHUNK_BYTES, Ab + tq * (int64_t)SYM_TILE_BYTES + (int64_t)ch * CHUNK_BYTES,
+                          (uint32_t)CHUNK_BYTES, &bars[stage], pol_stream);
         };
         if (lane == 0)
             for (int64_t qi = 0; qi < NSTAGE && qi < nch; ++qi) issue(qi);
@@ -166,20 +181,22 @@ k_spmv_sym(GridDev g, const double2 *__restrict__ A, const double *__restrict__ 
                 const int ddx = s % 3 - 1, ddy = (s / 3) % 3 - 1, ddz = s / 9 - 1;
                 const int64_t off = ddx + NX * ddy + npl * ddz;
                 const int64_t j = ln - off;
-                const double x0 = __ldg(p0 - off), x1 = __ldg(p1 - off), x2 = __ldg(p2 - off);
-                if (j >= 0 && j < g.ntiles * TILE_NODES) {
-                    const double *bj = Ad + (j >> 5) * SYM_TILE_DOUBLES + (j & 31) * 2;
-                    double m[9];
+                // branch-free: outside the operator (below the first tile / beyond the last) the
+                // vector operand is zeroed and the block is read from a valid dummy location, so
+                // the loads of all 13 slots can be in flight together
+                const bool okj = j >= 0 && j < g.ntiles * TILE_NODES;
+                const int64_t jc = okj ? j : ln;
+                const double x0 = okj ? __ldg(p0 - off) : 0., x1 = okj ? __ldg(p1 - off) : 0., x2 = okj ? __ldg(p2 - off) : 0.;
+                const double2 *bj = reinterpret_cast<const double2 *>(Ad) + (jc >> 5) * (SYM_PAIRS * TILE_NODES) + (jc & 31);
+                const int k0s = (s - 13) * 9;
+                double2 pr[5];
 #pragma unroll
-                    for (int e = 0; e < 9; ++e) {
-                        const int kp = (s - 13) * 9 + e;
-                        m[e] = __ldg(bj + (kp >> 1) * (TILE_NODES * 2) + (kp & 1));
-                    }
-                    // w_i[c] += sum_r A[j][s][r][c] * p_j[r]
-                    a0 = fma(m[0], x0, a0); a0 = fma(m[3], x1, a0); a0 = fma(m[6], x2, a0);
-                    a1 = fma(m[1], x0, a1); a1 = fma(m[4], x1, a1); a1 = fma(m[7], x2, a1);
-                    a2 = fma(m[2], x0, a2); a2 = fma(m[5], x1, a2); a2 = fma(m[8], x2, a2);
-                }
+                for (int e = 0; e < 5; ++e) pr[e] = ldg_hint(bj + ((k0s >> 1) + e) * TILE_NODES, pol_again);
+                const double *m = reinterpret_cast<const double *>(pr) + (k0s & 1);
+                // w_i[c] += sum_r A[j][s][r][c] * p_j[r]
+                a0 = fma(m[0], x0, a0); a0 = fma(m[3], x1, a0); a0 = fma(m[6], x2, a0);
+                a1 = fma(m[1], x0, a1); a1 = fma(m[4], x1, a1); a1 = fma(m[7], x2, a1);
+                a2 = fma(m[2], x0, a2); a2 = fma(m[5], x1, a2); a2 = fma(m[8], x2, a2);
             }
             // (2) own upper blocks (slots 13..26) from the TMA ring
 #pragma unroll
