@@ -850,26 +850,28 @@ static int apply_operator(macroc_ctx *c, int op, double *p, double *w, bool with
         int blocks;
         if (op == MACROC_OP_ASSEMBLED_SYM) {
             const int64_t tpp = (g.npl + TILE_NODES - 1) / TILE_NODES, rt = (g.NX + TILE_NODES - 1) / TILE_NODES;
-            const int64_t pencils = rt * ((((tpp + rt - 1) / rt) + 8 - 1) / 8);
-            int nseg = (int)std::max<int64_t>(1, (148 * 7 + pencils - 1) / pencils);
-            const int64_t mtot = (g.ntiles + tpp - 1) / tpp;
-            static const int sym_nseg = getenv("MACROC_SYM_NSEG") ? atoi(getenv("MACROC_SYM_NSEG")) : 0;
-            if (sym_nseg > 0) nseg = sym_nseg;
-            nseg = (int)std::min<int64_t>(nseg, std::max<int64_t>(1, mtot / 8));     // segments of >= 8 planes
             static const int sym_variant = getenv("MACROC_SYM_VARIANT") ? atoi(getenv("MACROC_SYM_VARIANT")) : 0;
             static const int sym_hint = getenv("MACROC_SYM_HINT") ? atoi(getenv("MACROC_SYM_HINT")) : 1;
-            auto go = [&](auto kern_dot, auto kern_nodot, int ns, int per_sm) {
-                const int smem = 8 * ns * CHUNK_BYTES + 8 * ns * 8 + 8 * 8;
+            static const int sym_nseg = getenv("MACROC_SYM_NSEG") ? atoi(getenv("MACROC_SYM_NSEG")) : 0;
+            const int64_t mtot = (g.ntiles + tpp - 1) / tpp;
+            auto go = [&](auto kern_dot, auto kern_nodot, int warps, int ns, int per_sm) {
+                const int64_t pencils = rt * ((((tpp + rt - 1) / rt) + warps - 1) / warps);
+                int nseg = sym_nseg > 0 ? sym_nseg : (int)std::max<int64_t>(1, (148 * 7 + pencils - 1) / pencils);
+                nseg = (int)std::min<int64_t>(nseg, std::max<int64_t>(1, mtot / 8));     // segments of >= 8 planes
+                const int smem = warps * ns * CHUNK_BYTES + warps * ns * 8 + warps * 8;
                 cudaFuncSetAttribute(kern_dot, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
                 cudaFuncSetAttribute(kern_nodot, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
                 blocks = (int)std::min<int64_t>(pencils * nseg, (int64_t)148 * per_sm);
-                if (with_dot) kern_dot<<<blocks, 256, smem, c->stream>>>(g, c->Asym, p, w, first, count, tpp, rt, nseg, c->partial + nparts, done, sym_hint);
-                else kern_nodot<<<blocks, 256, smem, c->stream>>>(g, c->Asym, p, w, first, count, tpp, rt, nseg, c->partial + nparts, done, sym_hint);
+                if (with_dot) kern_dot<<<blocks, warps * 32, smem, c->stream>>>(g, c->Asym, p, w, first, count, tpp, rt, nseg, c->partial + nparts, done, sym_hint);
+                else kern_nodot<<<blocks, warps * 32, smem, c->stream>>>(g, c->Asym, p, w, first, count, tpp, rt, nseg, c->partial + nparts, done, sym_hint);
                 c->launches++;
             };
-            if (sym_variant == 1) go(k_spmv_sym<8, 2, 2, true>, k_spmv_sym<8, 2, 2, false>, 2, 2);
-            else if (sym_variant == 2) go(k_spmv_sym<8, 3, 1, true>, k_spmv_sym<8, 3, 1, false>, 3, 1);
-            else go(k_spmv_sym<8, 4, 1, true>, k_spmv_sym<8, 4, 1, false>, 4, 1);
+            if (sym_variant == 1) go(k_spmv_sym<8, 2, 2, true>, k_spmv_sym<8, 2, 2, false>, 8, 2, 2);
+            else if (sym_variant == 2) go(k_spmv_sym<8, 3, 1, true>, k_spmv_sym<8, 3, 1, false>, 8, 3, 1);
+            else if (sym_variant == 3) go(k_spmv_sym<4, 7, 1, true>, k_spmv_sym<4, 7, 1, false>, 4, 7, 1);
+            else if (sym_variant == 4) go(k_spmv_sym<6, 5, 1, true>, k_spmv_sym<6, 5, 1, false>, 6, 5, 1);
+            else if (sym_variant == 5) go(k_spmv_sym<4, 4, 2, true>, k_spmv_sym<4, 4, 2, false>, 4, 4, 2);
+            else go(k_spmv_sym<8, 4, 1, true>, k_spmv_sym<8, 4, 1, false>, 8, 4, 1);
         } else if (mf) {
             // node ranges are whole planes here
             const int k0 = (int)(first / g.npl), k1 = (int)((first + count) / g.npl);
