@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
 k_spmv_sym(GridDev g, const double2 *__restrict__ A, const double *__restrict__ p, double *__restrict__ w,
            int64_t tile0, int64_t ntiles_range, int64_t tpp /* tiles per plane (rounded up) */,
            int64_t rt /* tiles per x-row (rounded up) */, int nseg, double *__restrict__ partial,
-           const int *__restrict__ done, int hint /* L2 policy: stream = hint / 4, second use = hint % 4 */)
+           const int *__restrict__ done, int hint /* L2 policies, 2 bits each: [1:0] z-1 gathers, [3:2] stream, [5:4] same-plane gathers */)
 {
     static_assert(NSTAGE >= 2 && NSTAGE <= SYM_CHUNKS, "ring depth");
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -134,7 +134,8 @@ k_spmv_sym(GridDev g, const double2 *__restrict__ A, const double *__restrict__ 
     const double *Ad = reinterpret_cast<const double *>(A);
     // every block is used twice: streamed by the TMA engine with its own tile, then read once
     // more as the transposed block of a neighbour.  After the second use the line is dead.
-    const uint64_t pol_stream = l2_policy(hint >> 2), pol_again = l2_policy(hint & 3);
+    const uint64_t pol_stream = l2_policy((hint >> 2) & 3), pol_again = l2_policy(hint & 3);
+    const uint64_t pol_plane = l2_policy((hint >> 4) & 3);
     const int64_t NX = g.NX, npl = g.npl;
     const int64_t tile_end = tile0 + ntiles_range;
     // work items: pencil (x-tile xt, block of WARPS rows yb) x z-segment; column of warp = xt + rt*(yb*WARPS + warp)
@@ -191,7 +192,7 @@ k_spmv_sym(GridDev g, const double2 *__restrict__ A, const double *__restrict__ 
                 const int k0s = (s - 13) * 9;
                 double2 pr[5];
 #pragma unroll
-                for (int e = 0; e < 5; ++e) pr[e] = ldg_hint(bj + ((k0s >> 1) + e) * TILE_NODES, pol_again);
+                for (int e = 0; e < 5; ++e) pr[e] = ldg_hint(bj + ((k0s >> 1) + e) * TILE_NODES, ddz ? pol_again : pol_plane);
                 const double *m = reinterpret_cast<const double *>(pr) + (k0s & 1);
                 // w_i[c] += sum_r A[j][s][r][c] * p_j[r]
                 a0 = fma(m[0], x0, a0); a0 = fma(m[3], x1, a0); a0 = fma(m[6], x2, a0);
