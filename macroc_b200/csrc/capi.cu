@@ -7,6 +7,7 @@
 // halo exchange and the CG dot-product all-reduces.
 // No CPU fallback: compute entry points return MACROC_ERR_NO_DEVICE without a GPU.
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -120,7 +121,7 @@ static inline int cdiv64(int64_t a, int64_t b) { return (int)((a + b - 1) / b); 
 // device; a context re-binds its element constants whenever another context used them last.
 // (Contexts are not thread-safe against each other on one device: one host thread per GPU, like
 // one MPI rank per DMDA box in the reference.)
-static uint64_t g_next_ctx_id = 1;
+static std::atomic<uint64_t> g_next_ctx_id{1};
 static uint64_t g_const_owner[64] = {0};
 static int bind_constants(macroc_ctx *c)
 {
@@ -514,6 +515,7 @@ static int allreduce_sums(macroc_ctx *c, int n)
 extern "C" double macroc_get_displacement(const macroc_ctx *ctx, int time_s)
 {
     // bcs.c:52-58 (intended value; the reference function lacks its return)
+    if (!ctx) return NAN;
     double time = time_s * ctx->cfg.dt;
     return -1.0 * (time / ctx->cfg.final_time);
 }
@@ -859,8 +861,12 @@ static int apply_operator(macroc_ctx *c, int op, double *p, double *w, bool with
                 int nseg = sym_nseg > 0 ? sym_nseg : (int)std::max<int64_t>(1, (148 * 7 + pencils - 1) / pencils);
                 nseg = (int)std::min<int64_t>(nseg, std::max<int64_t>(1, mtot / 8));     // segments of >= 8 planes
                 const int smem = warps * ns * CHUNK_BYTES + warps * ns * 8 + warps * 8;
-                cudaFuncSetAttribute(kern_dot, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-                cudaFuncSetAttribute(kern_nodot, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+                static bool configured[64] = {false};          // function attributes are per device (one variant per process)
+                if (!configured[c->device & 63]) {
+                    cudaFuncSetAttribute(kern_dot, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+                    cudaFuncSetAttribute(kern_nodot, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+                    configured[c->device & 63] = true;
+                }
                 blocks = (int)std::min<int64_t>(pencils * nseg, (int64_t)148 * per_sm);
                 if (with_dot) kern_dot<<<blocks, warps * 32, smem, c->stream>>>(g, c->Asym, p, w, first, count, tpp, rt, nseg, c->partial + nparts, done, sym_hint);
                 else kern_nodot<<<blocks, warps * 32, smem, c->stream>>>(g, c->Asym, p, w, first, count, tpp, rt, nseg, c->partial + nparts, done, sym_hint);
@@ -1187,6 +1193,8 @@ extern "C" int macroc_matmult(macroc_ctx *c, int op, const double *x_host, doubl
     if (!c || !x_host || !y_host) return MACROC_ERR_ARG;
     CU(c, cudaSetDevice(c->device));
     { int _rc = bind_constants(c); if (_rc) return _rc; }
+    if (op != MACROC_OP_ASSEMBLED && op != MACROC_OP_MATRIX_FREE && op != MACROC_OP_ASSEMBLED_SYM)
+        FAIL(c, MACROC_ERR_ARG, "matmult: unknown operator %d", op);
     if (op == MACROC_OP_ASSEMBLED && !c->A_valid) FAIL(c, MACROC_ERR_ARG, "matmult: no assembled operator");
     if (op == MACROC_OP_ASSEMBLED_SYM && !c->Asym_valid) FAIL(c, MACROC_ERR_ARG, "matmult: no symmetric operator");
     int64_t n = macroc_local_ndof(c);
