@@ -185,14 +185,35 @@ k_spmv_sym(GridDev g, const double2 *__restrict__ A, const double *__restrict__ 
                 // branch-free: outside the operator (below the first tile / beyond the last) the
                 // vector operand is zeroed and the block is read from a valid dummy location, so
                 // the loads of all 13 slots can be in flight together
+#ifndef MACROC_SYM_PROBE
                 const bool okj = j >= 0 && j < g.ntiles * TILE_NODES;
+#else
+                // measurement build only (make EXTRA=-DMACROC_SYM_PROBE; results are wrong): hint bit 8
+                // drops the gathers whose block was streamed by this CTA, bit 9 the ones streamed by
+                // another CTA / an earlier z segment
+                bool okj = j >= 0 && j < g.ntiles * TILE_NODES;
+                if (hint & 0x300) {
+                    const bool intra = (lane - ddx) >= 0 && (lane - ddx) < 32 && (warp - ddy) >= 0 && (warp - ddy) < WARPS &&
+                                       (ddz == 0 || mm > 0);
+                    if (((hint & 0x100) && intra) || ((hint & 0x200) && !intra)) okj = false;
+                }
+#endif
                 const int64_t jc = okj ? j : ln;
                 const double x0 = okj ? __ldg(p0 - off) : 0., x1 = okj ? __ldg(p1 - off) : 0., x2 = okj ? __ldg(p2 - off) : 0.;
                 const double2 *bj = reinterpret_cast<const double2 *>(Ad) + (jc >> 5) * (SYM_PAIRS * TILE_NODES) + (jc & 31);
                 const int k0s = (s - 13) * 9;
                 double2 pr[5];
+#ifndef MACROC_SYM_PROBE
 #pragma unroll
                 for (int e = 0; e < 5; ++e) pr[e] = ldg_hint(bj + ((k0s >> 1) + e) * TILE_NODES, ddz ? pol_again : pol_plane);
+#else
+#pragma unroll
+                for (int e = 0; e < 5; ++e) pr[e] = make_double2(0., 0.);
+                if (okj || !(hint & 0x300)) {
+#pragma unroll
+                    for (int e = 0; e < 5; ++e) pr[e] = ldg_hint(bj + ((k0s >> 1) + e) * TILE_NODES, ddz ? pol_again : pol_plane);
+                }
+#endif
                 const double *m = reinterpret_cast<const double *>(pr) + (k0s & 1);
                 // w_i[c] += sum_r A[j][s][r][c] * p_j[r]
                 a0 = fma(m[0], x0, a0); a0 = fma(m[3], x1, a0); a0 = fma(m[6], x2, a0);
