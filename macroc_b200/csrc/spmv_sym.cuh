@@ -118,12 +118,12 @@ k_spmv_sym(GridDev g, const double2 *__restrict__ A, const double *__restrict__ 
            const int *__restrict__ done, int hint /* L2 policies, 2 bits each: [1:0] z-1 gathers, [3:2] stream, [5:4] same-plane gathers */)
 {
     static_assert(NSTAGE >= 2 && NSTAGE <= SYM_CHUNKS, "ring depth");
-    extern __shared__ __align__(128) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_ring[];
     if (done && *done) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    unsigned char *ring = smem_raw + (size_t)warp * NSTAGE * CHUNK_BYTES;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + (size_t)WARPS * NSTAGE * CHUNK_BYTES) + warp * NSTAGE;
-    double *red = reinterpret_cast<double *>(smem_raw + (size_t)WARPS * NSTAGE * CHUNK_BYTES + (size_t)WARPS * NSTAGE * 8);
+    unsigned char *ring = smem_ring + (size_t)warp * NSTAGE * CHUNK_BYTES;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_ring + (size_t)WARPS * NSTAGE * CHUNK_BYTES) + warp * NSTAGE;
+    double *red = reinterpret_cast<double *>(smem_ring + (size_t)WARPS * NSTAGE * CHUNK_BYTES + (size_t)WARPS * NSTAGE * 8);
     if (lane == 0) {
 #pragma unroll
         for (int s = 0; s < NSTAGE; ++s) mbar_init(&bars[s], 1);

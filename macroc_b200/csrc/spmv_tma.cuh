@@ -77,12 +77,12 @@ k_spmv_tma(GridDev g, const double2 *__restrict__ A, const double *__restrict__ 
            int64_t tile0, int64_t ntiles, double *__restrict__ partial, const int *__restrict__ done)
 {
     static_assert(NSTAGE >= 2 && NSTAGE < CHUNKS_PER_TILE, "ring depth");
-    extern __shared__ __align__(128) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_ring[];
     if (done && *done) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    unsigned char *ring = smem_raw + (size_t)warp * NSTAGE * CHUNK_BYTES;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + SpmvTmaSmem<WARPS, NSTAGE>::ring_bytes) + warp * NSTAGE;
-    double *red = reinterpret_cast<double *>(smem_raw + SpmvTmaSmem<WARPS, NSTAGE>::ring_bytes +
+    unsigned char *ring = smem_ring + (size_t)warp * NSTAGE * CHUNK_BYTES;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_ring + SpmvTmaSmem<WARPS, NSTAGE>::ring_bytes) + warp * NSTAGE;
+    double *red = reinterpret_cast<double *>(smem_ring + SpmvTmaSmem<WARPS, NSTAGE>::ring_bytes +
                                              SpmvTmaSmem<WARPS, NSTAGE>::bar_bytes);
     if (lane == 0) {
 #pragma unroll
