@@ -1233,7 +1233,7 @@ extern "C" int macroc_write_pvtu(macroc_ctx *c, const char *file_prefix)
     if (s.rank == 0) {
         snprintf(name, sizeof(name), "%s.pvtu", file_prefix);
         FILE *fp = fopen(name, "w");
-        if (!fp) FAIL(c, 65, "write_pvtu: cannot open %s", name);
+        if (!fp) FAIL(c, 65, "write_pvtu: cannot open %.400s", name);
         fprintf(fp,
                 "<?xml version=\"1.0\"?>\n"
                 "<VTKFile type=\"PUnstructuredGrid\" version=\"0.1\" byte_order=\"LittleEndian\">\n"
@@ -1287,7 +1287,7 @@ extern "C" int macroc_write_pvtu(macroc_ctx *c, const char *file_prefix)
 
     snprintf(name, sizeof(name), "%s-subdo-%d.vtu", file_prefix, s.rank);
     FILE *fp = fopen(name, "w");
-    if (!fp) FAIL(c, 65, "write_pvtu: cannot open %s", name);
+    if (!fp) FAIL(c, 65, "write_pvtu: cannot open %.400s", name);
     fprintf(fp,
             "<?xml version=\"1.0\"?>\n"
             "<VTKFile type=\"UnstructuredGrid\" version=\"0.1\" byte_order=\"LittleEndian\">\n"
