@@ -41,7 +41,8 @@ enum { MACROC_BC_BENDING = 0, MACROC_BC_CIRCLE = 1 };          /* include/macroc
 enum { MACROC_VEC_U = 0, MACROC_VEC_DU = 1, MACROC_VEC_B = 2 }; /* include/macroc.h:128 */
 enum { MACROC_OP_ASSEMBLED = 0, MACROC_OP_MATRIX_FREE = 1,
        MACROC_OP_ASSEMBLED_SYM = 2 };  /* assembled, symmetric storage: 14 of the 27 slots
-                                          (opt-in; uniform tangent, one rank in this round) */
+                                          (opt-in; uniform tangent; one rank -- several ranks only
+                                          with MACROC_SYM_MULTIRANK=1 until validated on hardware) */
 /* where the Gauss-point stress / tangent come from (the MicroPP boundary) */
 enum { MACROC_MAT_UNIFORM = 0,   /* sigma = D eps, C = D in registers (north_star's fixed D)    */
        MACROC_MAT_PER_GP = 1 };  /* device arrays strain/stress[ngp*6], ctan[ngp*36], gpi=ie*8+gp */

@@ -42,7 +42,9 @@ struct macroc_ctx {
     ncclComm_t comm = nullptr;
     double *vec[V_COUNT] = {nullptr};
     double2 *A = nullptr;
-    double2 *Asym = nullptr;         // symmetric storage (14 of 27 slots), MACROC_OP_ASSEMBLED_SYM
+    double2 *Asym = nullptr;         // symmetric storage (14 of 27 slots), MACROC_OP_ASSEMBLED_SYM; points at tile 0
+    double2 *Asym_alloc = nullptr;   // start of the allocation: Asym_front tiles of the ghost plane below, then the slab
+    int64_t Asym_front = 0;
     bool A_valid = false, mf_ready = false, Asym_valid = false;
     double *Ke = nullptr, *T = nullptr;
     uint8_t *nodemask = nullptr, *ghostflag = nullptr;
@@ -268,7 +270,7 @@ static int ctx_free(macroc_ctx *c)
     if (c->comm) ncclCommDestroy(c->comm);
     for (cudaGraphExec_t ge : c->cg_graph) if (ge) cudaGraphExecDestroy(ge);
     for (int i = 0; i < V_COUNT; ++i) cudaFree(c->vec[i]);
-    cudaFree(c->A); cudaFree(c->Asym); cudaFree(c->Ke); cudaFree(c->T); cudaFree(c->nodemask); cudaFree(c->bc_idx); cudaFree(c->bc_coef);
+    cudaFree(c->A); cudaFree(c->Asym_alloc); cudaFree(c->Ke); cudaFree(c->T); cudaFree(c->nodemask); cudaFree(c->bc_idx); cudaFree(c->bc_coef);
     cudaFree(c->partial); cudaFree(c->sums); cudaFree(c->sc); cudaFree(c->stage); cudaFree(c->strain); cudaFree(c->stress);
     cudaFree(c->ctan); cudaFree(c->scratch); cudaFree(c->consts); cudaFree(c->gp_halo); cudaFree(c->ghostflag); cudaFree(c->xy_halo);
     if (c->device >= 0 && c->device < 64 && g_const_owner[c->device] == c->id) g_const_owner[c->device] = 0;
@@ -732,20 +734,38 @@ static int ensure_operator_storage(macroc_ctx *c)
     return MACROC_OK;
 }
 
+// Symmetric storage: uniform tangent only.  Several ranks (ghost-plane copy in front of tile 0) are
+// implemented but have not run on hardware yet: opt in with MACROC_SYM_MULTIRANK=1.
+static int sym_supported(macroc_ctx *c)
+{
+    if (c->cfg.material != MACROC_MAT_UNIFORM)
+        FAIL(c, MACROC_ERR_UNSUPPORTED, "symmetric operator storage needs the uniform tangent");
+    if (c->comm) {
+        const char *v = getenv("MACROC_SYM_MULTIRANK");
+        if (!v || atoi(v) == 0)
+            FAIL(c, MACROC_ERR_UNSUPPORTED, "symmetric operator storage: one rank only (several ranks: MACROC_SYM_MULTIRANK=1, unvalidated)");
+    }
+    return MACROC_OK;
+}
+
 extern "C" int macroc_assembly_jac(macroc_ctx *c)
 {
     if (!c) return MACROC_ERR_ARG;
     CU(c, cudaSetDevice(c->device));
     { int _rc = bind_constants(c); if (_rc) return _rc; }
     if (c->cfg.op == MACROC_OP_ASSEMBLED_SYM) {
-        if (c->cfg.material != MACROC_MAT_UNIFORM || c->comm)
-            FAIL(c, MACROC_ERR_UNSUPPORTED, "symmetric operator storage: uniform tangent on one rank only (this round)");
-        if (!c->Asym) {
-            size_t bytes = (size_t)SYM_TILE_BYTES * (size_t)c->g.ntiles;
-            cudaError_t e = cudaMalloc(&c->Asym, bytes);
+        int rc = sym_supported(c);
+        if (rc) return rc;
+        if (!c->Asym_alloc) {
+            // a lower z neighbour: keep a private copy of the ghost plane's dz = +1 blocks in front of tile 0
+            c->Asym_front = c->slab.has_lower() ? (c->g.npl + TILE_NODES - 1) / TILE_NODES : 0;
+            size_t bytes = (size_t)SYM_TILE_BYTES * (size_t)(c->g.ntiles + c->Asym_front);
+            cudaError_t e = cudaMalloc(&c->Asym_alloc, bytes);
             if (e != cudaSuccess) { cudaGetLastError(); FAIL(c, MACROC_ERR_MEM, "operator needs %.2f GB of device memory", bytes / 1e9); }
+            c->Asym = c->Asym_alloc + c->Asym_front * (int64_t)(SYM_PAIRS * TILE_NODES);
         }
-        LAUNCH(c, k_fill_operator_sym, cdiv64(c->g.ntiles, 8), 256, c->g, c->T, c->nodemask, c->Asym, c->vec[V_DINV]);
+        LAUNCH(c, k_fill_operator_sym, cdiv64(c->g.ntiles + c->Asym_front, 8), 256, c->g, c->T, c->nodemask, c->Asym, c->vec[V_DINV],
+               -c->Asym_front);
         c->Asym_valid = true;
     } else if (c->cfg.op == MACROC_OP_MATRIX_FREE) {
         if (c->cfg.material != MACROC_MAT_UNIFORM) FAIL(c, MACROC_ERR_UNSUPPORTED, "matrix-free operator needs the uniform tangent");
@@ -868,8 +888,8 @@ static int apply_operator(macroc_ctx *c, int op, double *p, double *w, bool with
                     configured[c->device & 63] = true;
                 }
                 blocks = (int)std::min<int64_t>(pencils * nseg, (int64_t)148 * per_sm);
-                if (with_dot) kern_dot<<<blocks, warps * 32, smem, c->stream>>>(g, c->Asym, p, w, first, count, tpp, rt, nseg, c->partial + nparts, done, sym_hint);
-                else kern_nodot<<<blocks, warps * 32, smem, c->stream>>>(g, c->Asym, p, w, first, count, tpp, rt, nseg, c->partial + nparts, done, sym_hint);
+                if (with_dot) kern_dot<<<blocks, warps * 32, smem, c->stream>>>(g, c->Asym, p, w, first, count, tpp, rt, nseg, c->partial + nparts, done, -c->Asym_front * TILE_NODES, sym_hint);
+                else kern_nodot<<<blocks, warps * 32, smem, c->stream>>>(g, c->Asym, p, w, first, count, tpp, rt, nseg, c->partial + nparts, done, -c->Asym_front * TILE_NODES, sym_hint);
                 c->launches++;
             };
             if (sym_variant == 1) go(k_spmv_sym<8, 2, 2, true>, k_spmv_sym<8, 2, 2, false>, 8, 2, 2);
@@ -1037,8 +1057,7 @@ extern "C" int macroc_solve_Ax(macroc_ctx *c, int *its, double *rnorm)
 extern "C" int macroc_set_operator(macroc_ctx *c, int op)
 {
     if (!c || (op != MACROC_OP_ASSEMBLED && op != MACROC_OP_MATRIX_FREE && op != MACROC_OP_ASSEMBLED_SYM)) return MACROC_ERR_ARG;
-    if (op == MACROC_OP_ASSEMBLED_SYM && (c->cfg.material != MACROC_MAT_UNIFORM || c->comm))
-        FAIL(c, MACROC_ERR_UNSUPPORTED, "symmetric operator storage: uniform tangent on one rank only (this round)");
+    if (op == MACROC_OP_ASSEMBLED_SYM) { int rc = sym_supported(c); if (rc) return rc; }
     if (op == MACROC_OP_MATRIX_FREE && c->cfg.material != MACROC_MAT_UNIFORM)
         FAIL(c, MACROC_ERR_UNSUPPORTED, "matrix-free operator needs the uniform tangent");
     c->cfg.op = op;
@@ -1178,7 +1197,7 @@ extern "C" int macroc_get_matrix_blocks(macroc_ctx *c, double *host)
     const int64_t nown = (int64_t)c->g.xm * c->g.ym * c->g.nzl;
     for (int64_t n0 = 0; n0 < nown; n0 += chunk) {
         int64_t nn = std::min<int64_t>(chunk, nown - n0);
-        if (sym) LAUNCH(c, k_export_blocks_sym, cdiv64(nn * 243, 256), 256, c->g, reinterpret_cast<const double *>(c->Asym), n0, nn, tmp);
+        if (sym) LAUNCH(c, k_export_blocks_sym, cdiv64(nn * 243, 256), 256, c->g, reinterpret_cast<const double *>(c->Asym), n0, nn, tmp, -c->Asym_front * TILE_NODES);
         else LAUNCH(c, k_export_blocks, cdiv64(nn * 243, 256), 256, c->g, reinterpret_cast<const double *>(c->A), n0, nn, tmp);
         cudaError_t e = cudaMemcpyAsync(host + n0 * 243, tmp, sizeof(double) * 243 * nn, cudaMemcpyDeviceToHost, c->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);

@@ -14,6 +14,13 @@
 // moments earlier by the same CTA when the traversal keeps z- and y-neighbours close, so they
 // hit L2: a CTA owns a "pencil" (one x-tile, 8 consecutive rows, one warp per row) and sweeps
 // it upward in z.  The traversal only affects locality, never the result.
+//
+// Several ranks: the blocks of a lower neighbour that lives in the ghost plane below the slab
+// (z = zs-1) are not local rows, but for a uniform tangent they are a function of node class and
+// Dirichlet masks only, so the rank keeps its own copy: `front` extra tiles in front of tile 0
+// hold the dz = +1 slots of the ghost plane (node ln < 0 sits in tile floor(ln / 32), lane ln & 31).
+// Ghost columns / rows of x / y neighbours are ordinary local nodes and need nothing special: a
+// block towards an owned node only sums elements adjacent to that owned node, all of them local.
 #pragma once
 
 #include "kernels.cuh"
@@ -37,17 +44,19 @@ __device__ __forceinline__ double sym_entry(const double *__restrict__ A, int64_
 // Jacobian "assembly" for a uniform tangent into the symmetric layout (cf. k_fill_operator).
 __global__ void __launch_bounds__(256)
 k_fill_operator_sym(GridDev g, const double *__restrict__ T, const uint8_t *__restrict__ nodemask,
-                    double2 *__restrict__ A, double *__restrict__ dinv)
+                    double2 *__restrict__ A, double *__restrict__ dinv, int64_t tile_lo /* <= 0: first tile, ghost plane below */)
 {
-    int64_t tile = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    int64_t tile = tile_lo + (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (tile >= g.ntiles) return;
     int lane = threadIdx.x & 31;
     int64_t ln = tile * TILE_NODES + lane;
-    bool valid = ln < g.nloc;
+    // ln < 0: node of the ghost plane below the slab (only its dz = +1 slots are ever read)
+    bool valid = ln < g.nloc && ln >= -g.npl && (ln >= 0 || g.zs > 0);
     int type = 13;
     unsigned own = 0;
     if (valid) {
-        int i = (int)(ln % g.NX), j = (int)((ln / g.NX) % g.NY), k = (int)(ln / g.npl) + g.zs;
+        const int64_t lg = ln + g.npl;                           // >= 0: index from the start of the ghost plane
+        int i = (int)(lg % g.NX), j = (int)((lg / g.NX) % g.NY), k = (int)(lg / g.npl) - 1 + g.zs;
         type = node_class(i, g.NX) + 3 * node_class(j, g.NY) + 9 * node_class(k, g.NZ);
         own = nodemask[g.G + ln];
     }
@@ -60,7 +69,7 @@ k_fill_operator_sym(GridDev g, const double *__restrict__ T, const uint8_t *__re
         const int slot = 13 + kp / 9, rr = (kp % 9) / 3, cc = kp % 3;
         const int ddx = slot % 3 - 1, ddy = (slot / 3) % 3 - 1, ddz = slot / 9 - 1;
         double v = 0.;
-        if (valid) {
+        if (valid && (ln >= 0 || ddz == 1)) {
             v = __ldg(Tt + slot * 9 + 3 * rr + cc);
             unsigned nb = nodemask[g.G + ln + ddx + (int64_t)g.NX * ddy + g.npl * ddz];
             if (((own >> rr) & 1u) || ((nb >> cc) & 1u)) v = (slot == 13 && rr == cc) ? 1. : 0.;
@@ -69,7 +78,7 @@ k_fill_operator_sym(GridDev g, const double *__restrict__ T, const uint8_t *__re
         if (kp & 1) At[(kp >> 1) * TILE_NODES] = make_double2(carry, v);
         else carry = v;
     }
-    if (valid) {
+    if (valid && ln >= 0) {
 #pragma unroll
         for (int d = 0; d < 3; ++d) dinv[d * g.S + g.G + ln] = diag[d] != 0. ? 1. / diag[d] : 1.;
     }
@@ -77,7 +86,7 @@ k_fill_operator_sym(GridDev g, const double *__restrict__ T, const uint8_t *__re
 
 // full 27-slot view of owned nodes from the symmetric storage (export / tests)
 __global__ void k_export_blocks_sym(GridDev g, const double *__restrict__ A, int64_t node0, int64_t nnodes,
-                                    double *__restrict__ out /* [nnodes][243] */)
+                                    double *__restrict__ out /* [nnodes][243] */, int64_t jmin /* first stored node (<= 0) */)
 {
     int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= nnodes * 243) return;
@@ -89,7 +98,7 @@ __global__ void k_export_blocks_sym(GridDev g, const double *__restrict__ A, int
         // block (i, s) = transpose of block (i + off_s, 26 - s), stored with node i + off_s
         const int ddx = slot % 3 - 1, ddy = (slot / 3) % 3 - 1, ddz = slot / 9 - 1;
         const int64_t j = ln + ddx + (int64_t)g.NX * ddy + g.npl * ddz;
-        v = j >= 0 ? sym_entry(A, j, (26 - slot - 13) * 9 + 3 * cc + rr) : 0.;
+        v = j >= jmin ? sym_entry(A, j, (26 - slot - 13) * 9 + 3 * cc + rr) : 0.;
     }
     out[e] = v;
 }
@@ -115,7 +124,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
 k_spmv_sym(GridDev g, const double2 *__restrict__ A, const double *__restrict__ p, double *__restrict__ w,
            int64_t tile0, int64_t ntiles_range, int64_t tpp /* tiles per plane (rounded up) */,
            int64_t rt /* tiles per x-row (rounded up) */, int nseg, double *__restrict__ partial,
-           const int *__restrict__ done, int hint /* L2 policies, 2 bits each: [1:0] z-1 gathers, [3:2] stream, [5:4] same-plane gathers */)
+           const int *__restrict__ done, int64_t jmin /* first stored node: 0, or -(front tiles * 32) */,
+           int hint /* L2 policies, 2 bits each: [1:0] z-1 gathers, [3:2] stream, [5:4] same-plane gathers */)
 {
     static_assert(NSTAGE >= 2 && NSTAGE <= SYM_CHUNKS, "ring depth");
     extern __shared__ __align__(128) unsigned char smem_ring[];
@@ -186,12 +196,12 @@ k_spmv_sym(GridDev g, const double2 *__restrict__ A, const double *__restrict__ 
                 // vector operand is zeroed and the block is read from a valid dummy location, so
                 // the loads of all 13 slots can be in flight together
 #ifndef MACROC_SYM_PROBE
-                const bool okj = j >= 0 && j < g.ntiles * TILE_NODES;
+                const bool okj = j >= jmin && j < g.ntiles * TILE_NODES;
 #else
                 // measurement build only (make EXTRA=-DMACROC_SYM_PROBE; results are wrong): hint bit 8
                 // drops the gathers whose block was streamed by this CTA, bit 9 the ones streamed by
                 // another CTA / an earlier z segment
-                bool okj = j >= 0 && j < g.ntiles * TILE_NODES;
+                bool okj = j >= jmin && j < g.ntiles * TILE_NODES;
                 if (hint & 0x300) {
                     const bool intra = (lane - ddx) >= 0 && (lane - ddx) < 32 && (warp - ddy) >= 0 && (warp - ddy) < WARPS &&
                                        (ddz == 0 || mm > 0);

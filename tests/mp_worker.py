@@ -95,8 +95,10 @@ def gpu_mode(args):
     if os.environ.get("MACROC_TEST_CASES") == "boxes":      # only the 2-D / 3-D processor grids
         cases = [c for c in cases if sum(1 for q in c[5] if q != 1) >= 2]
     for (NX, NY, NZ, bc, extra, pg) in cases:
-        for op, material in ((M.OP_ASSEMBLED, M.MAT_UNIFORM), (M.OP_MATRIX_FREE, M.MAT_UNIFORM),
-                             (M.OP_ASSEMBLED, M.MAT_PER_GP)):
+        variants = [(M.OP_ASSEMBLED, M.MAT_UNIFORM), (M.OP_MATRIX_FREE, M.MAT_UNIFORM), (M.OP_ASSEMBLED, M.MAT_PER_GP)]
+        if os.environ.get("MACROC_SYM_MULTIRANK", "0") != "0":   # symmetric storage on several ranks (opt-in)
+            variants.append((M.OP_ASSEMBLED_SYM, M.MAT_UNIFORM))
+        for op, material in variants:
             box = [M.get_unique_id() if rank == 0 else None]
             dist.broadcast_object_list(box, src=0)
             ts = 3
@@ -111,10 +113,11 @@ def gpu_mode(args):
             xs0, ys0, zs0, xm, ym, zm = p["corners"]
             box = np.zeros((NZ, NY, NX), bool); box[zs0:zs0 + zm, ys0:ys0 + ym, xs0:xs0 + xm] = True
             nodes = np.flatnonzero(box.reshape(-1))            # owned nodes, x fastest inside the box
-            if op == M.OP_ASSEMBLED:
+            assembled = op in (M.OP_ASSEMBLED, M.OP_ASSEMBLED_SYM)
+            if assembled:
                 m.set_strains(); m.homogenize(); m.assembly_jac()
             y_loc = m.matmult(x.reshape(-1, 3)[nodes].reshape(-1), op)
-            A_loc = m.get_matrix_blocks() if op == M.OP_ASSEMBLED else None
+            A_loc = m.get_matrix_blocks() if assembled else None
             eps_loc = None
             if material == M.MAT_UNIFORM and op == M.OP_ASSEMBLED:
                 m.set_vec(M.VEC_U, u_loc)                    # strains of the converged displacement
@@ -138,11 +141,14 @@ def gpu_mode(args):
                 assert rel_err(u, o.get_vec("u")) < 1e-9, (NX, NY, NZ, bc, op, rel_err(u, o.get_vec("u")))
                 o.assembly_jac()
                 assert rel_err(y, o.matmult(x)) < 1e-13
-                if op == M.OP_ASSEMBLED:
+                if assembled:
                     A = np.zeros((NX * NY * NZ, 27, 3, 3))
                     for g in got:
                         A[g[5]] = g[2]
-                    if material == M.MAT_UNIFORM:
+                    if op == M.OP_ASSEMBLED_SYM:             # stored half bitwise, mirrored half to rounding
+                        assert np.array_equal(A[:, 13:], o.block_stencil()[:, 13:])
+                        assert rel_err(A, o.block_stencil()) < 1e-14
+                    elif material == M.MAT_UNIFORM:
                         assert np.array_equal(A, o.block_stencil())
                     else:
                         assert rel_err(A, o.block_stencil()) < 1e-12
