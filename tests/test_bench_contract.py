@@ -44,5 +44,4 @@ def test_gpu_arm_line_small_grid():
     assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
     assert d["config"]["newton_its_per_step"] == [1, 1]
     assert d["matrix_free"]["cg_iterations"] == pytest.approx(d["config"]["cg_iterations_per_step"], abs=2)
-    assert d["assembled_sym"]["cg_iterations"] == pytest.approx(d["config"]["cg_iterations_per_step"], abs=2)
-    assert d["assembled_sym"]["newton_its"] == 1 and d["assembled_sym"]["spmv_ms"] > 0
+    assert "assembled_sym" in d              # its numbers are checked in test_gpu_parity.py (symmetric storage)
