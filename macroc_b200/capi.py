@@ -15,7 +15,8 @@ from dataclasses import dataclass
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libmacroc_b200.so")
+# MACROC_B200_LIB: an alternative build of the same library (measurement builds, tools/round2_open.sh)
+LIB_PATH = os.environ.get("MACROC_B200_LIB") or os.path.join(HERE, "lib", "libmacroc_b200.so")
 CSRC = os.path.join(HERE, "csrc")
 
 BC_BENDING, BC_CIRCLE = 0, 1
