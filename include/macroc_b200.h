@@ -40,9 +40,7 @@ extern "C" {
 enum { MACROC_BC_BENDING = 0, MACROC_BC_CIRCLE = 1 };          /* include/macroc.h:58 */
 enum { MACROC_VEC_U = 0, MACROC_VEC_DU = 1, MACROC_VEC_B = 2 }; /* include/macroc.h:128 */
 enum { MACROC_OP_ASSEMBLED = 0, MACROC_OP_MATRIX_FREE = 1,
-       MACROC_OP_ASSEMBLED_SYM = 2 };  /* assembled, symmetric storage: 14 of the 27 slots
-                                          (opt-in; uniform tangent; one rank -- several ranks only
-                                          with MACROC_SYM_MULTIRANK=1 until validated on hardware) */
+       MACROC_OP_ASSEMBLED_SYM = 2 };  /* assembled, symmetric storage: 14 of the 27 slots */
 /* where the Gauss-point stress / tangent come from (the MicroPP boundary) */
 enum { MACROC_MAT_UNIFORM = 0,   /* sigma = D eps, C = D in registers (north_star's fixed D)    */
        MACROC_MAT_PER_GP = 1 };  /* device arrays strain/stress[ngp*6], ctan[ngp*36], gpi=ie*8+gp */
@@ -52,6 +50,7 @@ enum { MACROC_JAC_AUTO = 0,      /* uniform D: class-stencil fill; per-GP: eleme
 enum {
     MACROC_KSP_CONVERGED_RTOL = 2, MACROC_KSP_CONVERGED_ATOL = 3,
     MACROC_KSP_DIVERGED_ITS = -3, MACROC_KSP_DIVERGED_DTOL = -4,
+    MACROC_KSP_DIVERGED_INDEFINITE_PC = -8, MACROC_KSP_DIVERGED_NANORINF = -9,
     MACROC_KSP_DIVERGED_INDEFINITE_MAT = -10
 };
 
@@ -100,6 +99,12 @@ int macroc_config_from_args(macroc_config *cfg, int argc, const char *const *arg
 /* 128-byte NCCL unique id for multi-rank contexts; rank 0 creates it, the host
  * ships it to the other ranks by any means (file, torch.distributed, MPI). */
 int macroc_get_unique_id(void *id128);
+/* In-process ranks instead of NCCL (csrc/loopback.h): returns an id that makes the `nranks`
+ * contexts created with it -- each by its own host thread, on one device or several -- talk
+ * through device-to-device copies and a rank-ordered host sum.  Every multi-rank code path
+ * (slabs, general boxes, halos, ghost-plane tiles) runs unchanged; used to check decomposition
+ * independence (reference tests/CMakeLists.txt:21-28) on a single GPU.  Not a performance path. */
+int macroc_loopback_id(int nranks, void *id128);
 int macroc_create(const macroc_config *cfg, int rank, int nranks, const void *id128,
                   macroc_ctx **out);
 int macroc_destroy(macroc_ctx *ctx);

@@ -7,5 +7,5 @@ Dirichlet treatment (src/bcs.c) and the CG+Jacobi solve inside the Newton loop
 from .capi import (  # noqa: F401
     BC_BENDING, BC_CIRCLE, JAC_AUTO, JAC_ELEMENT, MAT_PER_GP, MAT_UNIFORM, OP_ASSEMBLED, OP_ASSEMBLED_SYM, OP_MATRIX_FREE,
     VEC_B, VEC_DU, VEC_U,
-    Config, MacroC, MacrocError, bc_lists, build, calc_B, get_unique_id, lib, partition,
+    Config, MacroC, MacrocError, bc_lists, build, calc_B, get_unique_id, lib, loopback_id, partition,
 )

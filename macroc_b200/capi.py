@@ -37,6 +37,7 @@ EXPORTS = [
     "macroc_time_kernel", "macroc_launch_count", "macroc_device_synchronize", "macroc_version",
     "macroc_event_record", "macroc_event_elapsed_ms", "macroc_profile_enable", "macroc_profile_get",
     "macroc_homogenize", "macroc_gp_arrays", "macroc_set_gp_data", "macroc_set_operator", "macroc_write_pvtu",
+    "macroc_loopback_id",
 ]
 
 
@@ -95,6 +96,7 @@ def lib():
     L.macroc_default_config.argtypes = [C.POINTER(CConfig)]
     L.macroc_config_from_args.argtypes = [C.POINTER(CConfig), C.c_int, C.POINTER(C.c_char_p)]
     L.macroc_get_unique_id.argtypes = [C.c_void_p]
+    L.macroc_loopback_id.argtypes = [C.c_int, C.c_void_p]
     L.macroc_create.argtypes = [C.POINTER(CConfig), C.c_int, C.c_int, C.c_void_p, C.POINTER(vp)]
     L.macroc_destroy.argtypes = [vp]
     L.macroc_last_error.argtypes = [vp]
@@ -242,6 +244,16 @@ def get_unique_id() -> bytes:
     rc = lib().macroc_get_unique_id(buf)
     if rc:
         raise MacrocError(rc, lib().macroc_last_error(None).decode())
+    return buf.raw
+
+
+def loopback_id(nranks: int) -> bytes:
+    """Id of an in-process communicator: `nranks` MacroC objects created with it, each driven by
+    its own host thread, stand in for `nranks` ranks on one GPU (decomposition tests)."""
+    buf = C.create_string_buffer(128)
+    rc = lib().macroc_loopback_id(nranks, buf)
+    if rc:
+        raise MacrocError(rc, "macroc_loopback_id")
     return buf.raw
 
 

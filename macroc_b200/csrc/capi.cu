@@ -12,6 +12,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -24,6 +26,7 @@
 #include "spmv_tma.cuh"
 #include "assembly_elem.cuh"
 #include "spmv_sym.cuh"
+#include "loopback.h"
 
 using namespace macroc;
 
@@ -40,6 +43,7 @@ struct macroc_ctx {
     cudaStream_t stream = nullptr, comm_stream = nullptr;
     cudaEvent_t ev_ready = nullptr, ev_halo = nullptr, ev_t0 = nullptr, ev_t1 = nullptr, ev_chk[2] = {nullptr, nullptr};
     ncclComm_t comm = nullptr;
+    LoopGroup *loop = nullptr;       // in-process communicator (loopback.h) instead of NCCL
     double *vec[V_COUNT] = {nullptr};
     double2 *A = nullptr;
     double2 *Asym = nullptr;         // symmetric storage (14 of 27 slots), MACROC_OP_ASSEMBLED_SYM; points at tile 0
@@ -51,6 +55,7 @@ struct macroc_ctx {
     double *xy_halo = nullptr;       // 4 send + 4 receive staging buffers of the x / y halo
     size_t xy_halo_stride = 0;
     double *consts = nullptr;        // device copy of {dsh[192], D[36], T[6561]} for bind_constants
+    std::vector<double> consts_host; // the same values on the host (compared on an owner change)
     uint64_t id = 0;
     int64_t *bc_idx = nullptr;
     double *bc_coef = nullptr;
@@ -119,21 +124,63 @@ struct macroc_ctx {
 
 static inline int cdiv64(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
-// __constant__ symbols are per device and shared by every context of the process on that
-// device; a context re-binds its element constants whenever another context used them last.
-// (Contexts are not thread-safe against each other on one device: one host thread per GPU, like
-// one MPI rank per DMDA box in the reference.)
+// __constant__ symbols (c_dsh, c_D, c_T) are per device and shared by every context of the
+// process on that device.  ConstLease is held for the duration of every entry point that
+// launches kernels reading them:
+//   * contexts whose constants are byte-identical (the ranks of a loopback group, repeated runs
+//     of one configuration) share the symbols, also from different host threads;
+//   * a context with different constants waits until no such entry point is in flight, drains
+//     the device (kernels of the previous owner may still be running: set_strains, assembly_jac
+//     and update_u return without a sync), uploads its own values synchronously and takes over.
 static std::atomic<uint64_t> g_next_ctx_id{1};
-static uint64_t g_const_owner[64] = {0};
-static int bind_constants(macroc_ctx *c)
+struct ConstSlot {
+    std::mutex mu;
+    std::condition_variable cv;
+    int users = 0;                   // entry points in flight that read the symbols
+    uint64_t owner = 0;              // context whose values are bound (0: none)
+    std::vector<double> content;     // the bound values
+};
+static ConstSlot g_const_slot[64];
+
+static int const_acquire(macroc_ctx *c)
 {
-    if (c->device >= 0 && c->device < 64 && g_const_owner[c->device] == c->id) return MACROC_OK;
-    CU(c, cudaMemcpyToSymbolAsync(c_dsh, c->consts, sizeof(double) * 192, 0, cudaMemcpyDeviceToDevice, c->stream));
-    CU(c, cudaMemcpyToSymbolAsync(c_D, c->consts + 192, sizeof(double) * 36, 0, cudaMemcpyDeviceToDevice, c->stream));
-    CU(c, cudaMemcpyToSymbolAsync(c_T, c->consts + 228, sizeof(double) * 27 * 243, 0, cudaMemcpyDeviceToDevice, c->stream));
-    if (c->device >= 0 && c->device < 64) g_const_owner[c->device] = c->id;
+    ConstSlot &sl = g_const_slot[c->device & 63];
+    std::unique_lock<std::mutex> lk(sl.mu);
+    if (sl.content != c->consts_host) {
+        sl.cv.wait(lk, [&] { return sl.users == 0 || sl.content == c->consts_host; });
+        if (sl.content != c->consts_host) {
+            cudaError_t e = cudaDeviceSynchronize();          // the previous owner's kernels
+            if (e == cudaSuccess) e = cudaMemcpyToSymbol(c_dsh, c->consts_host.data(), sizeof(double) * 192);
+            if (e == cudaSuccess) e = cudaMemcpyToSymbol(c_D, c->consts_host.data() + 192, sizeof(double) * 36);
+            if (e == cudaSuccess) e = cudaMemcpyToSymbol(c_T, c->consts_host.data() + 228, sizeof(double) * 27 * 243);
+            if (e == cudaSuccess) e = cudaDeviceSynchronize();
+            if (e != cudaSuccess) {
+                sl.content.clear(); sl.owner = 0;
+                FAIL(c, MACROC_ERR_CUDA, "binding the element constants: %s", cudaGetErrorString(e));
+            }
+            sl.content = c->consts_host;
+        }
+    }
+    sl.owner = c->id;
+    sl.users++;
     return MACROC_OK;
 }
+static void const_release(macroc_ctx *c)
+{
+    ConstSlot &sl = g_const_slot[c->device & 63];
+    std::lock_guard<std::mutex> lk(sl.mu);
+    if (sl.users > 0) sl.users--;
+    if (sl.users == 0) sl.cv.notify_all();
+}
+struct ConstLease {
+    macroc_ctx *c;
+    int rc;
+    explicit ConstLease(macroc_ctx *ctx) : c(ctx), rc(const_acquire(ctx)) {}
+    ~ConstLease() { if (rc == MACROC_OK) const_release(c); }
+    ConstLease(const ConstLease &) = delete;
+    ConstLease &operator=(const ConstLease &) = delete;
+};
+#define BIND_CONSTANTS(ctx) ConstLease _lease(ctx); if (_lease.rc) return _lease.rc
 
 extern "C" int macroc_version(void) { return 100; }
 
@@ -252,6 +299,17 @@ extern "C" int macroc_get_unique_id(void *id128)
     return MACROC_OK;
 }
 
+extern "C" int macroc_loopback_id(int nranks, void *id128)
+{
+    if (!id128 || nranks < 2) return MACROC_ERR_ARG;
+    LoopGroup *grp = new LoopGroup(nranks);
+    if (const char *v = getenv("MACROC_LOOPBACK_TIMEOUT")) grp->timeout_s = std::max(1, atoi(v));
+    memset(id128, 0, 128);
+    memcpy(id128, LoopGroup::MAGIC, 16);
+    memcpy((unsigned char *)id128 + 16, &grp, sizeof(grp));
+    return MACROC_OK;
+}
+
 static void isotropic_D(double E, double nu, double *D)
 {
     double lambda = E * nu / ((1. + nu) * (1. - 2. * nu));
@@ -268,12 +326,28 @@ static int ctx_free(macroc_ctx *c)
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->comm) ncclCommDestroy(c->comm);
+    if (c->loop) {
+        // the last member to leave frees the group; a member that leaves early breaks it for the rest
+        LoopGroup *grp = c->loop;
+        LoopGroup::Member &me = grp->m[(size_t)c->slab.rank];
+        bool last;
+        {
+            std::lock_guard<std::mutex> lk(grp->mu);
+            grp->left++;
+            last = grp->left == grp->joined;
+            if (!last) { grp->broken = true; grp->cv.notify_all(); }
+        }
+        if (me.ev_ready) cudaEventDestroy(me.ev_ready);
+        if (me.ev_done) cudaEventDestroy(me.ev_done);
+        me.ev_ready = me.ev_done = nullptr;
+        if (last) { if (grp->host_part) cudaFreeHost(grp->host_part); delete grp; }
+        c->loop = nullptr;
+    }
     for (cudaGraphExec_t ge : c->cg_graph) if (ge) cudaGraphExecDestroy(ge);
     for (int i = 0; i < V_COUNT; ++i) cudaFree(c->vec[i]);
     cudaFree(c->A); cudaFree(c->Asym_alloc); cudaFree(c->Ke); cudaFree(c->T); cudaFree(c->nodemask); cudaFree(c->bc_idx); cudaFree(c->bc_coef);
     cudaFree(c->partial); cudaFree(c->sums); cudaFree(c->sc); cudaFree(c->stage); cudaFree(c->strain); cudaFree(c->stress);
     cudaFree(c->ctan); cudaFree(c->scratch); cudaFree(c->consts); cudaFree(c->gp_halo); cudaFree(c->ghostflag); cudaFree(c->xy_halo);
-    if (c->device >= 0 && c->device < 64 && g_const_owner[c->device] == c->id) g_const_owner[c->device] = 0;
     cudaFree(c->flush);
     if (c->sums_host) cudaFreeHost(c->sums_host);
     if (c->sc_host) cudaFreeHost(c->sc_host);
@@ -299,6 +373,16 @@ extern "C" int macroc_create(const macroc_config *cfg, int rank, int nranks, con
     if (cfg->bc_type != MACROC_BC_BENDING && cfg->bc_type != MACROC_BC_CIRCLE)
         FAIL((macroc_ctx *)nullptr, MACROC_ERR_ARG, "macroc_create: bc_type must be 0 or 1");
     if (nranks > 1 && !id128) FAIL((macroc_ctx *)nullptr, MACROC_ERR_ARG, "macroc_create: nranks > 1 needs a unique id");
+    if (cfg->op != MACROC_OP_ASSEMBLED && cfg->op != MACROC_OP_MATRIX_FREE && cfg->op != MACROC_OP_ASSEMBLED_SYM)
+        FAIL((macroc_ctx *)nullptr, MACROC_ERR_ARG, "macroc_create: unknown operator %d", (int)cfg->op);
+    if (cfg->material != MACROC_MAT_UNIFORM && cfg->material != MACROC_MAT_PER_GP)
+        FAIL((macroc_ctx *)nullptr, MACROC_ERR_ARG, "macroc_create: unknown material source %d", (int)cfg->material);
+    if (cfg->jac_mode != MACROC_JAC_AUTO && cfg->jac_mode != MACROC_JAC_ELEMENT)
+        FAIL((macroc_ctx *)nullptr, MACROC_ERR_ARG, "macroc_create: unknown jac_mode %d", (int)cfg->jac_mode);
+    if (cfg->ksp_maxits < 0 || cfg->newton_max_its < 0)
+        FAIL((macroc_ctx *)nullptr, MACROC_ERR_ARG, "macroc_create: negative iteration limit");
+    if (cfg->material == MACROC_MAT_PER_GP && cfg->op != MACROC_OP_ASSEMBLED)
+        FAIL((macroc_ctx *)nullptr, MACROC_ERR_UNSUPPORTED, "macroc_create: per-Gauss-point tangents need the assembled operator");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
         cudaGetLastError();
@@ -415,19 +499,29 @@ extern "C" int macroc_create(const macroc_config *cfg, int rank, int nranks, con
         if (cfg->use_D) memcpy(D, cfg->D, sizeof(D)); else isotropic_D(cfg->E, cfg->nu, D);
         CUC(cudaMalloc(&c->consts, sizeof(double) * (228 + 27 * 243)));
         CUC(cudaMemcpyAsync(c->consts + 192, D, sizeof(D), cudaMemcpyHostToDevice, c->stream));
-        CUC(cudaMemcpyToSymbolAsync(c_D, D, sizeof(D), 0, cudaMemcpyHostToDevice, c->stream));
         const bool phys = cfg->physical_B != 0;
         LAUNCH(c, k_make_dsh, 1, 64, c->consts, phys ? c->geo.dx : 1., phys ? c->geo.dy : 1., phys ? c->geo.dz : 1.);
-        CUC(cudaMemcpyToSymbolAsync(c_dsh, c->consts, sizeof(double) * 192, 0, cudaMemcpyDeviceToDevice, c->stream));
-        LAUNCH(c, k_element_matrix, 3, 192, c->geo.wg, c->Ke);
+        LAUNCH(c, k_element_matrix, 3, 192, c->consts, c->consts + 192, c->geo.wg, c->Ke);
         LAUNCH(c, k_stencil_table, cdiv64(27 * 243, 256), 256, c->Ke, c->T);
         CUC(cudaMemcpyAsync(c->consts + 228, c->T, sizeof(double) * 27 * 243, cudaMemcpyDeviceToDevice, c->stream));
-        CUC(cudaMemcpyToSymbolAsync(c_T, c->T, sizeof(double) * 27 * 243, 0, cudaMemcpyDeviceToDevice, c->stream));
-        if (c->device >= 0 && c->device < 64) g_const_owner[c->device] = c->id;
+        // the __constant__ copies are bound by the first entry point that needs them (ConstLease)
+        c->consts_host.resize(228 + 27 * 243);
+        CUC(cudaMemcpyAsync(c->consts_host.data(), c->consts, sizeof(double) * c->consts_host.size(), cudaMemcpyDeviceToHost, c->stream));
         CUC(cudaStreamSynchronize(c->stream));
         CUC(cudaGetLastError());
     }
-    if (nranks > 1) {
+    if (nranks > 1 && is_loopback_id(id128)) {
+        // in-process ranks (loopback.h): join the group, meet the other members once
+        LoopGroup *grp = loopback_group_of(id128);
+        if (!grp || grp->n != nranks) { g_last_error = "macroc_create: loopback id was made for another rank count"; ctx_free(c); return MACROC_ERR_ARG; }
+        LoopGroup::Member &me = grp->m[(size_t)rank];
+        CUC(cudaEventCreateWithFlags(&me.ev_ready, cudaEventDisableTiming));
+        CUC(cudaEventCreateWithFlags(&me.ev_done, cudaEventDisableTiming));
+        me.device = c->device;
+        { std::lock_guard<std::mutex> lk(grp->mu); grp->joined++; }
+        c->loop = grp;
+        if (!grp->barrier()) { g_last_error = "macroc_create: loopback group did not assemble (every rank needs its own host thread)"; ctx_free(c); return MACROC_ERR_NCCL; }
+    } else if (nranks > 1) {
         ncclUniqueId id;
         memcpy(&id, id128, 128);
         ncclResult_t e = ncclCommInitRank(&c->comm, nranks, id, rank);
@@ -442,6 +536,47 @@ extern "C" int macroc_create(const macroc_config *cfg, int rank, int nranks, con
 // halo + reductions
 // ---------------------------------------------------------------------------
 
+static inline bool has_comm(const macroc_ctx *c) { return c->comm != nullptr || c->loop != nullptr; }
+
+// One grouped exchange with the neighbours: NCCL send/recv, or the loopback rendezvous.  Matching
+// is by order per peer pair, like ncclSend/ncclRecv inside one group.  Every rank of the
+// communicator must reach the same sequence of exchanges (the call sites below skip an exchange
+// only on conditions that are global: a processor-grid extent of 1).
+static int comm_exchange(macroc_ctx *c, const std::vector<LoopXfer> &sends, const std::vector<LoopXfer> &recvs, cudaStream_t st)
+{
+    if (c->comm) {
+        if (sends.empty() && recvs.empty()) return MACROC_OK;
+        NC(c, ncclGroupStart());
+        for (const LoopXfer &x : sends) NC(c, ncclSend(x.buf, x.cnt, ncclDouble, x.peer, c->comm, st));
+        for (const LoopXfer &x : recvs) NC(c, ncclRecv(x.buf, x.cnt, ncclDouble, x.peer, c->comm, st));
+        NC(c, ncclGroupEnd());
+        return MACROC_OK;
+    }
+    LoopGroup *grp = c->loop;
+    if (!grp) return MACROC_OK;
+    const int me = c->slab.rank;
+    LoopGroup::Member &mine = grp->m[(size_t)me];
+    mine.sends = sends;
+    CU(c, cudaEventRecord(mine.ev_ready, st));                    // my send buffers are final after this point of `st`
+    if (!grp->barrier()) FAIL(c, MACROC_ERR_NCCL, "loopback exchange: a rank is missing (timeout or failure of another rank)");
+    std::vector<size_t> taken((size_t)grp->n, 0);
+    for (const LoopXfer &r : recvs) {
+        const LoopGroup::Member &src = grp->m[(size_t)r.peer];
+        const LoopXfer *match = nullptr;
+        size_t seen = 0;
+        for (const LoopXfer &sx : src.sends)
+            if (sx.peer == me && seen++ == taken[(size_t)r.peer]) { match = &sx; break; }
+        if (!match || match->cnt != r.cnt) { grp->fail(); FAIL(c, MACROC_ERR_NCCL, "loopback exchange: rank %d has no matching send for rank %d", r.peer, me); }
+        taken[(size_t)r.peer]++;
+        CU(c, cudaStreamWaitEvent(st, src.ev_ready, 0));
+        CU(c, cudaMemcpyAsync(r.buf, match->buf, sizeof(double) * r.cnt, cudaMemcpyDefault, st));
+    }
+    CU(c, cudaEventRecord(mine.ev_done, st));                     // everything I had to fetch is enqueued before this
+    if (!grp->barrier()) FAIL(c, MACROC_ERR_NCCL, "loopback exchange: a rank is missing (timeout or failure of another rank)");
+    for (const LoopXfer &x : sends) CU(c, cudaStreamWaitEvent(st, grp->m[(size_t)x.peer].ev_done, 0));   // do not overwrite before it was read
+    return MACROC_OK;
+}
+
 // x / y phases of DMGlobalToLocal for a general DMDA box: the owned boundary column (row) of the
 // owned planes goes to the neighbour's ghost column (row).  Run x, then y (rows include the x
 // ghost columns just received), then z (planes include both): edge and corner ghosts arrive
@@ -450,10 +585,10 @@ static int halo_exchange_xy(macroc_ctx *c, double *v, cudaStream_t st)
 {
     const GridDev &g = c->g;
     const Slab &s = c->slab;
-    if (!c->comm || !s.xy_split()) return MACROC_OK;
+    if (!has_comm(c) || !s.xy_split()) return MACROC_OK;
     for (int axis = 0; axis < 2; ++axis) {
+        if ((axis == 0 ? s.px : s.py) == 1) continue;             // global: no rank has a neighbour along this axis
         const int lo = s.nb[2 * axis], hi = s.nb[2 * axis + 1];
-        if (lo < 0 && hi < 0) continue;
         const int len = axis == 0 ? g.NY : g.NX, ext = axis == 0 ? g.NX : g.NY;
         const int first_owned = axis == 0 ? g.ox0 : g.oy0, last_owned = first_owned + (axis == 0 ? g.xm : g.ym) - 1;
         const size_t cnt = (size_t)3 * g.nzl * len;
@@ -462,10 +597,11 @@ static int halo_exchange_xy(macroc_ctx *c, double *v, cudaStream_t st)
         const int blocks = cdiv64((int64_t)cnt, 256);
         if (lo >= 0) { k_halo_pack_xy<<<blocks, 256, 0, st>>>(g, v, sb_lo, axis, first_owned, 1); c->launches++; }
         if (hi >= 0) { k_halo_pack_xy<<<blocks, 256, 0, st>>>(g, v, sb_hi, axis, last_owned, 1); c->launches++; }
-        NC(c, ncclGroupStart());
-        if (lo >= 0) { NC(c, ncclSend(sb_lo, cnt, ncclDouble, lo, c->comm, st)); NC(c, ncclRecv(rb_lo, cnt, ncclDouble, lo, c->comm, st)); }
-        if (hi >= 0) { NC(c, ncclSend(sb_hi, cnt, ncclDouble, hi, c->comm, st)); NC(c, ncclRecv(rb_hi, cnt, ncclDouble, hi, c->comm, st)); }
-        NC(c, ncclGroupEnd());
+        std::vector<LoopXfer> sends, recvs;
+        if (lo >= 0) { sends.push_back({lo, sb_lo, cnt}); recvs.push_back({lo, rb_lo, cnt}); }
+        if (hi >= 0) { sends.push_back({hi, sb_hi, cnt}); recvs.push_back({hi, rb_hi, cnt}); }
+        int rc = comm_exchange(c, sends, recvs, st);
+        if (rc) return rc;
         if (lo >= 0) { k_halo_pack_xy<<<blocks, 256, 0, st>>>(g, v, rb_lo, axis, 0, 0); c->launches++; }
         if (hi >= 0) { k_halo_pack_xy<<<blocks, 256, 0, st>>>(g, v, rb_hi, axis, ext - 1, 0); c->launches++; }
     }
@@ -476,24 +612,23 @@ static int halo_exchange_xy(macroc_ctx *c, double *v, cudaStream_t st)
 // and component over NCCL send/recv.
 static int halo_exchange_z(macroc_ctx *c, double *v, cudaStream_t st)
 {
-    if (!c->comm) return MACROC_OK;
+    if (!has_comm(c)) return MACROC_OK;
     const GridDev &g = c->g;
     const Slab &s = c->slab;
-    if (!s.has_lower() && !s.has_upper()) return MACROC_OK;
-    NC(c, ncclGroupStart());
+    if (s.pz == 1) return MACROC_OK;
+    std::vector<LoopXfer> sends, recvs;
     for (int d = 0; d < 3; ++d) {
         double *base = v + d * g.S + g.G;
         if (s.has_lower()) {
-            NC(c, ncclSend(base, (size_t)g.npl, ncclDouble, s.nb[4], c->comm, st));
-            NC(c, ncclRecv(base - g.npl, (size_t)g.npl, ncclDouble, s.nb[4], c->comm, st));
+            sends.push_back({s.nb[4], base, (size_t)g.npl});
+            recvs.push_back({s.nb[4], base - g.npl, (size_t)g.npl});
         }
         if (s.has_upper()) {
-            NC(c, ncclSend(base + g.nloc - g.npl, (size_t)g.npl, ncclDouble, s.nb[5], c->comm, st));
-            NC(c, ncclRecv(base + g.nloc, (size_t)g.npl, ncclDouble, s.nb[5], c->comm, st));
+            sends.push_back({s.nb[5], base + g.nloc - g.npl, (size_t)g.npl});
+            recvs.push_back({s.nb[5], base + g.nloc, (size_t)g.npl});
         }
     }
-    NC(c, ncclGroupEnd());
-    return MACROC_OK;
+    return comm_exchange(c, sends, recvs, st);
 }
 
 static int halo_exchange(macroc_ctx *c, double *v, cudaStream_t st)
@@ -503,10 +638,29 @@ static int halo_exchange(macroc_ctx *c, double *v, cudaStream_t st)
     return halo_exchange_z(c, v, st);
 }
 
+// sum of c->sums[0..n) over the ranks, in place, on the context's stream
 static int allreduce_sums(macroc_ctx *c, int n)
 {
-    if (!c->comm) return MACROC_OK;
-    NC(c, ncclAllReduce(c->sums, c->sums, (size_t)n, ncclDouble, ncclSum, c->comm, c->stream));
+    if (c->comm) {
+        NC(c, ncclAllReduce(c->sums, c->sums, (size_t)n, ncclDouble, ncclSum, c->comm, c->stream));
+        return MACROC_OK;
+    }
+    LoopGroup *grp = c->loop;
+    if (!grp) return MACROC_OK;
+    const int me = c->slab.rank;
+    if (me == 0 && !grp->host_part) CU(c, cudaMallocHost(&grp->host_part, sizeof(double) * 4 * (size_t)grp->n));
+    if (!grp->barrier()) FAIL(c, MACROC_ERR_NCCL, "loopback all-reduce: a rank is missing");
+    CU(c, cudaMemcpyAsync(grp->host_part + 4 * me, c->sums, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    if (!grp->barrier()) FAIL(c, MACROC_ERR_NCCL, "loopback all-reduce: a rank is missing");
+    for (int q = 0; q < n; ++q) {
+        double acc = 0.;
+        for (int r = 0; r < grp->n; ++r) acc += grp->host_part[4 * r + q];     // rank order: bit-reproducible
+        c->sums_host[q] = acc;
+    }
+    if (!grp->barrier()) FAIL(c, MACROC_ERR_NCCL, "loopback all-reduce: a rank is missing");   // everyone has read the partials
+    CU(c, cudaMemcpyAsync(c->sums, c->sums_host, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));          // sums_host is reused by the callers
     return MACROC_OK;
 }
 
@@ -556,24 +710,26 @@ static int ensure_gp_arrays(macroc_ctx *c, bool need_ctan)
 // packed into / unpacked from a contiguous buffer.
 static int halo_gp_layer(macroc_ctx *c, double *arr, int nq)
 {
-    if (!c->comm) return MACROC_OK;
+    if (!has_comm(c)) return MACROC_OK;
     const Slab &s = c->slab;
     const int64_t lnex = s.lnex, lney = s.lney, nlay = c->er.nez_ext;
     const int64_t maxface = std::max({lney * nlay, lnex * nlay, lnex * lney});
     if (!c->gp_halo) CU(c, cudaMalloc(&c->gp_halo, sizeof(double) * 2 * (size_t)maxface * 288));
     double *sbuf = c->gp_halo, *rbuf = c->gp_halo + (size_t)maxface * 288;
     const int64_t owned[3] = {s.nex, s.ney, s.nez};          // DMDA-owned element layers per axis
+    const int pgrid[3] = {s.px, s.py, s.pz};
     for (int axis = 0; axis < 3; ++axis) {
+        if (pgrid[axis] == 1) continue;                       // global: nobody has a neighbour along this axis
         const int lo = s.nb[2 * axis], hi = s.nb[2 * axis + 1];
-        if (lo < 0 && hi < 0) continue;
         const int64_t face = axis == 0 ? lney * nlay : (axis == 1 ? lnex * nlay : lnex * lney);
         const size_t cnt = (size_t)face * nq;
         const int blocks = cdiv64((int64_t)cnt, 256);
         if (lo >= 0) LAUNCH(c, k_gp_face_copy, blocks, 256, nq, lnex, lney, nlay, axis, (int64_t)0, c->er.ne_ext, arr, sbuf, 1);
-        NC(c, ncclGroupStart());
-        if (lo >= 0) NC(c, ncclSend(sbuf, cnt, ncclDouble, lo, c->comm, c->stream));
-        if (hi >= 0) NC(c, ncclRecv(rbuf, cnt, ncclDouble, hi, c->comm, c->stream));
-        NC(c, ncclGroupEnd());
+        std::vector<LoopXfer> sends, recvs;
+        if (lo >= 0) sends.push_back({lo, sbuf, cnt});
+        if (hi >= 0) recvs.push_back({hi, rbuf, cnt});
+        int rc = comm_exchange(c, sends, recvs, c->stream);
+        if (rc) return rc;
         if (hi >= 0) LAUNCH(c, k_gp_face_copy, blocks, 256, nq, lnex, lney, nlay, axis, owned[axis], c->er.ne_ext, arr, rbuf, 0);
     }
     return MACROC_OK;
@@ -583,7 +739,7 @@ extern "C" int macroc_set_strains(macroc_ctx *c, int materialize)
 {
     if (!c) return MACROC_ERR_ARG;
     CU(c, cudaSetDevice(c->device));
-    { int _rc = bind_constants(c); if (_rc) return _rc; }
+    BIND_CONSTANTS(c);
     int rc = halo_exchange(c, c->vec[V_U], c->stream);
     if (rc) return rc;
     if (materialize || c->cfg.material == MACROC_MAT_PER_GP) {
@@ -603,7 +759,7 @@ extern "C" int macroc_homogenize(macroc_ctx *c)
     if (!c) return MACROC_ERR_ARG;
     if (c->cfg.material != MACROC_MAT_PER_GP) return MACROC_OK;
     CU(c, cudaSetDevice(c->device));
-    { int _rc = bind_constants(c); if (_rc) return _rc; }
+    BIND_CONSTANTS(c);
     int rc = ensure_gp_arrays(c, true);
     if (rc) return rc;
     if (c->ne_owned > 0)
@@ -709,7 +865,7 @@ extern "C" int macroc_assembly_res(macroc_ctx *c, double *norm)
 {
     if (!c) return MACROC_ERR_ARG;
     CU(c, cudaSetDevice(c->device));
-    { int _rc = bind_constants(c); if (_rc) return _rc; }
+    BIND_CONSTANTS(c);
     int nparts = 0;
     int rc = residual_launch(c, &nparts);
     if (rc) return rc;
@@ -740,11 +896,6 @@ static int sym_supported(macroc_ctx *c)
 {
     if (c->cfg.material != MACROC_MAT_UNIFORM)
         FAIL(c, MACROC_ERR_UNSUPPORTED, "symmetric operator storage needs the uniform tangent");
-    if (c->comm) {
-        const char *v = getenv("MACROC_SYM_MULTIRANK");
-        if (!v || atoi(v) == 0)
-            FAIL(c, MACROC_ERR_UNSUPPORTED, "symmetric operator storage: one rank only (several ranks: MACROC_SYM_MULTIRANK=1, unvalidated)");
-    }
     return MACROC_OK;
 }
 
@@ -752,7 +903,7 @@ extern "C" int macroc_assembly_jac(macroc_ctx *c)
 {
     if (!c) return MACROC_ERR_ARG;
     CU(c, cudaSetDevice(c->device));
-    { int _rc = bind_constants(c); if (_rc) return _rc; }
+    BIND_CONSTANTS(c);
     if (c->cfg.op == MACROC_OP_ASSEMBLED_SYM) {
         int rc = sym_supported(c);
         if (rc) return rc;
@@ -842,7 +993,7 @@ static int apply_operator(macroc_ctx *c, int op, double *p, double *w, bool with
                           bool fuse_pw_scalars = false)
 {
     const GridDev &g = c->g;
-    const bool comm = c->comm != nullptr;
+    const bool comm = has_comm(c);
     const bool mf = op == MACROC_OP_MATRIX_FREE;
     int64_t lo_end = 0, hi_begin = mf ? g.nloc : g.ntiles;     // interior range in nodes (mf) or tiles
     if (comm && g.nzl >= 3) {
@@ -943,7 +1094,7 @@ static int cg_iteration(macroc_ctx *c, int op)
     LAUNCH(c, k_cg_update_p, nb, 256, g, c->sc, c->vec[V_R], c->vec[V_DINV], c->vec[V_P]);
     const bool sample = c->prof_on && c->prof_used < macroc_ctx::PROF_RING && (c->prof_counter++ % c->prof_stride) == 0;
     if (sample) CU(c, cudaEventRecord(c->prof_ev[2 * c->prof_used], c->stream));
-    const bool single = c->comm == nullptr;      // no all-reduce between reduction and scalar update
+    const bool single = !has_comm(c);            // no all-reduce between reduction and scalar update
     int rc = apply_operator(c, op, c->vec[V_P], c->vec[V_W], true, &c->sc->done, single);
     if (rc) return rc;
     if (sample) { CU(c, cudaEventRecord(c->prof_ev[2 * c->prof_used + 1], c->stream)); c->prof_used++; }
@@ -985,7 +1136,7 @@ extern "C" int macroc_solve_Ax(macroc_ctx *c, int *its, double *rnorm)
 {
     if (!c) return MACROC_ERR_ARG;
     CU(c, cudaSetDevice(c->device));
-    { int _rc = bind_constants(c); if (_rc) return _rc; }
+    BIND_CONSTANTS(c);
     const int op = c->cfg.op;
     if (op == MACROC_OP_ASSEMBLED && !c->A_valid) FAIL(c, MACROC_ERR_ARG, "solve_Ax: assembly_jac has not been called");
     if (op == MACROC_OP_ASSEMBLED_SYM && !c->Asym_valid) FAIL(c, MACROC_ERR_ARG, "solve_Ax: assembly_jac has not been called");
@@ -1001,7 +1152,7 @@ extern "C" int macroc_solve_Ax(macroc_ctx *c, int *its, double *rnorm)
     // Launch-bound small grids (BASELINE configs[1]): after the first batch, `check` iterations are
     // replayed as one CUDA graph (all kernel arguments are iteration-invariant: the CG state lives
     // on the device).  Single rank only; not while the live profile brackets launches with events.
-    const bool use_graph = !c->comm && !c->prof_on && c->g.nloc <= ((int64_t)1 << 21);
+    const bool use_graph = !has_comm(c) && !c->prof_on && c->g.nloc <= ((int64_t)1 << 21);
     for (int it = 0; it < c->cfg.ksp_maxits + 1 && !finished; ++it) {
         if (use_graph && it >= check && it % check == 0) {
             if (!c->cg_graph[op]) {
@@ -1085,7 +1236,7 @@ extern "C" int macroc_calc_force(macroc_ctx *c, double *force)
 {
     if (!c || !force) return MACROC_ERR_ARG;
     CU(c, cudaSetDevice(c->device));
-    { int _rc = bind_constants(c); if (_rc) return _rc; }
+    BIND_CONSTANTS(c);
     const Slab &s = c->slab;
     { int _rc = halo_exchange(c, c->vec[V_U], c->stream); if (_rc) return _rc; }   // ghost nodes of u may be stale after update_u
     // forces.c:75 (bending: ranks that own the X = LX face) / :133 (circle: ghost start + owned
@@ -1211,7 +1362,7 @@ extern "C" int macroc_matmult(macroc_ctx *c, int op, const double *x_host, doubl
 {
     if (!c || !x_host || !y_host) return MACROC_ERR_ARG;
     CU(c, cudaSetDevice(c->device));
-    { int _rc = bind_constants(c); if (_rc) return _rc; }
+    BIND_CONSTANTS(c);
     if (op != MACROC_OP_ASSEMBLED && op != MACROC_OP_MATRIX_FREE && op != MACROC_OP_ASSEMBLED_SYM)
         FAIL(c, MACROC_ERR_ARG, "matmult: unknown operator %d", op);
     if (op == MACROC_OP_ASSEMBLED && !c->A_valid) FAIL(c, MACROC_ERR_ARG, "matmult: no assembled operator");
@@ -1245,7 +1396,7 @@ extern "C" int macroc_write_pvtu(macroc_ctx *c, const char *file_prefix)
 {
     if (!c || !file_prefix) return MACROC_ERR_ARG;
     CU(c, cudaSetDevice(c->device));
-    { int _rc = bind_constants(c); if (_rc) return _rc; }
+    BIND_CONSTANTS(c);
     const Slab &s = c->slab;
     const GridDev &g = c->g;
     char name[4096];
@@ -1422,7 +1573,7 @@ extern "C" int macroc_time_kernel(macroc_ctx *c, int what, int reps, int flush_l
 {
     if (!c || !ms_mean || reps <= 0) return MACROC_ERR_ARG;
     CU(c, cudaSetDevice(c->device));
-    { int _rc = bind_constants(c); if (_rc) return _rc; }
+    BIND_CONSTANTS(c);
     const GridDev &g = c->g;
     if ((what == 0 || what == 2) && !c->A_valid) FAIL(c, MACROC_ERR_ARG, "time_kernel: assemble first");
     if ((what == 8 || what == 9) && !c->Asym_valid) FAIL(c, MACROC_ERR_ARG, "time_kernel: assemble the symmetric operator first");

@@ -101,11 +101,11 @@ __global__ void k_make_dsh(double *out /* [8][8][3] */, double hx, double hy, do
     out[(gp * 8 + n) * 3 + 2] = __ddiv_rn(c_sgn[n][2] * __dmul_rn(fx, fy) / 8. * 2., hz);
 }
 
-__device__ __forceinline__ double Bentry(int gp, int row, int col)
+__device__ __forceinline__ double Bentry(const double *__restrict__ dsh, int gp, int row, int col)
 {
     // B[row][3n+d] of assembly.c:234-253
     int n = col / 3, d = col % 3;
-    const double *h = c_dsh[gp][n];
+    const double *h = dsh + (gp * 8 + n) * 3;
     switch (row) {
         case 0: return d == 0 ? h[0] : 0.;
         case 1: return d == 1 ? h[1] : 0.;
@@ -119,7 +119,10 @@ __device__ __forceinline__ double Bentry(int gp, int row, int col)
 // Ke = sum_gp B^T C B wg for a tangent that is the same at the 8 Gauss points
 // (assembly.c:87-101).  One thread per entry, the reference's summation order
 // (gp, k, l) and rounding (no FMA contraction) -> bitwise the CPU value.
-__global__ void k_element_matrix(double wg, double *Ke /* [24][24] */)
+// dsh, D: global-memory copies (the context's own; the __constant__ symbols may be bound to
+// another context while this one is being created).
+__global__ void k_element_matrix(const double *__restrict__ dsh /* [8][8][3] */, const double *__restrict__ D /* [36] */,
+                                 double wg, double *Ke /* [24][24] */)
 {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= 576) return;
@@ -127,9 +130,9 @@ __global__ void k_element_matrix(double wg, double *Ke /* [24][24] */)
     double acc = 0.;
     for (int gp = 0; gp < 8; ++gp)
         for (int k = 0; k < 6; ++k) {
-            double bki = Bentry(gp, k, i);
+            double bki = Bentry(dsh, gp, k, i);
             for (int l = 0; l < 6; ++l) {
-                double term = __dmul_rn(__dmul_rn(__dmul_rn(bki, c_D[k * 6 + l]), Bentry(gp, l, j)), wg);
+                double term = __dmul_rn(__dmul_rn(__dmul_rn(bki, D[k * 6 + l]), Bentry(dsh, gp, l, j)), wg);
                 acc = __dadd_rn(acc, term);
             }
         }
@@ -774,7 +777,8 @@ __global__ void k_cg_scalars_init(CgScalars *s, const double *sums /* zz, zr */)
     s->ttol = fmax(s->rtol * dp, s->abstol);
     s->beta = sums[1]; s->betaold = 1.;
     s->its = 0; s->done = 0; s->reason = 0;
-    if (dp <= s->ttol) { s->done = 1; s->reason = dp <= s->abstol ? 3 : 2; }
+    if (!isfinite(dp) || !isfinite(sums[1])) { s->done = 1; s->reason = -9; }        // KSPCheckNorm / KSPCheckDot
+    else if (dp <= s->ttol) { s->done = 1; s->reason = dp <= s->abstol ? 3 : 2; }
     else if (s->beta == 0.) { s->its = 1; s->done = 1; s->reason = 3; }
 }
 
@@ -846,20 +850,27 @@ k_cg_update_xr(GridDev g, const CgScalars *__restrict__ s, const double *__restr
 
 __device__ __forceinline__ void cg_scalars_pw_body(CgScalars *s, double pw)
 {
+    // KSPSolve_CG: KSPCheckDot(dpi) -> KSP_DIVERGED_NANORINF; dpi == 0 or a sign change against the
+    // previous dpi -> KSP_DIVERGED_INDEFINITE_MAT
+    const double old = s->pw;
+    const int i = s->its;
     s->pw = pw;
     s->its += 1;                               // ksp->its = i+1 at the top of the loop body
-    if (pw == 0.) { s->done = 1; s->reason = -10; }
+    if (!isfinite(pw)) { s->done = 1; s->reason = -9; }
+    else if (pw == 0. || (i > 0 && ((pw > 0.) != (old > 0.)))) { s->done = 1; s->reason = -10; }
 }
 
 __device__ __forceinline__ void cg_scalars_iter_body(CgScalars *s, double zz, double zr)
 {
     double dp = sqrt(zz);
     s->dp = dp;
+    if (!isfinite(dp) || !isfinite(zr)) { s->done = 1; s->reason = -9; return; }      // KSP_DIVERGED_NANORINF
     if (dp <= s->ttol) { s->done = 1; s->reason = dp <= s->abstol ? 3 : 2; return; }
     if (dp >= s->dtol * s->dp0) { s->done = 1; s->reason = -4; return; }
     if (s->its >= s->maxits) { s->done = 1; s->reason = -3; return; }
     s->betaold = s->beta;
     s->beta = zr;
+    if (zr < 0.) { s->done = 1; s->reason = -8; return; }             // KSP_DIVERGED_INDEFINITE_PC
     if (s->beta == 0.) { s->its += 1; s->done = 1; s->reason = 3; }   // KSP_CONVERGED_ATOL at the next top
 }
 
