@@ -197,6 +197,10 @@ int macroc_write_pvtu(macroc_ctx *ctx, const char *file_prefix);
  * flush_l2 != 0 writes a >L2 buffer between launches.  Clobbers b, du and the
  * KSP work vectors (2, 5) -- a measurement hook, not part of the solve path. */
 int macroc_time_kernel(macroc_ctx *ctx, int what, int reps, int flush_l2, double *ms_mean);
+/* Measured DFMA rate of the device (register-resident FMA chains, best of 5 launches), in
+ * TFLOP/s: the denominator of the FP64-pipe fractions quoted for the matrix-free apply and the
+ * element assembly (no FP64 figure is in MEASURED_PEAKS.json). */
+int macroc_fp64_probe(macroc_ctx *ctx, double *tflops);
 uint64_t macroc_launch_count(const macroc_ctx *ctx);       /* kernels launched so far */
 /* CUDA-event stopwatch on the context's stream (slots 0..7): record, then
  * elapsed(a, b) synchronises on b and returns the device time between them. */
@@ -207,6 +211,9 @@ int macroc_event_elapsed_ms(macroc_ctx *ctx, int slot_a, int slot_b, double *ms)
  * get returns the mean device time per application and the sample count. */
 int macroc_profile_enable(macroc_ctx *ctx, int enable, int stride);
 int macroc_profile_get(macroc_ctx *ctx, double *apply_ms_mean, int64_t *samples);
+/* ... and the device time of whole solve_Ax calls with their CG iteration count (the extra iterations
+ * launched after convergence are no-ops but are inside the time): ms per PCG iteration = ratio. */
+int macroc_profile_get_solve(macroc_ctx *ctx, double *solve_ms_total, int64_t *iterations);
 int macroc_device_synchronize(macroc_ctx *ctx);
 int macroc_version(void);
 

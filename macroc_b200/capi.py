@@ -37,7 +37,7 @@ EXPORTS = [
     "macroc_time_kernel", "macroc_launch_count", "macroc_device_synchronize", "macroc_version",
     "macroc_event_record", "macroc_event_elapsed_ms", "macroc_profile_enable", "macroc_profile_get",
     "macroc_homogenize", "macroc_gp_arrays", "macroc_set_gp_data", "macroc_set_operator", "macroc_write_pvtu",
-    "macroc_loopback_id",
+    "macroc_loopback_id", "macroc_fp64_probe", "macroc_profile_get_solve",
 ]
 
 
@@ -130,12 +130,14 @@ def lib():
     L.macroc_matmult.argtypes = [vp, C.c_int, C.c_void_p, C.c_void_p]
     L.macroc_get_strain_stress.argtypes = [vp, C.c_void_p, C.c_void_p, C.POINTER(C.c_int64)]
     L.macroc_time_kernel.argtypes = [vp, C.c_int, C.c_int, C.c_int, dp]
+    L.macroc_fp64_probe.argtypes = [vp, dp]
     L.macroc_launch_count.argtypes = [vp]; L.macroc_launch_count.restype = C.c_uint64
     L.macroc_device_synchronize.argtypes = [vp]
     L.macroc_event_record.argtypes = [vp, C.c_int]
     L.macroc_event_elapsed_ms.argtypes = [vp, C.c_int, C.c_int, dp]
     L.macroc_profile_enable.argtypes = [vp, C.c_int, C.c_int]
     L.macroc_profile_get.argtypes = [vp, dp, C.POINTER(C.c_int64)]
+    L.macroc_profile_get_solve.argtypes = [vp, dp, C.POINTER(C.c_int64)]
     L.macroc_version.restype = C.c_int
     _lib = L
     return L
@@ -397,6 +399,12 @@ class MacroC:
         self._chk(self._L.macroc_time_kernel(self._h, what, reps, int(flush_l2), C.byref(ms)))
         return ms.value
 
+    def fp64_probe(self) -> float:
+        """Measured DFMA rate of the device in TFLOP/s (register-resident FMA chains)."""
+        t = C.c_double()
+        self._chk(self._L.macroc_fp64_probe(self._h, C.byref(t)))
+        return t.value
+
     def event_record(self, slot: int):
         self._chk(self._L.macroc_event_record(self._h, slot))
 
@@ -411,6 +419,11 @@ class MacroC:
     def profile_get(self):
         ms, n = C.c_double(), C.c_int64()
         self._chk(self._L.macroc_profile_get(self._h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    def profile_get_solve(self):
+        ms, n = C.c_double(), C.c_int64()
+        self._chk(self._L.macroc_profile_get_solve(self._h, C.byref(ms), C.byref(n)))
         return ms.value, n.value
 
     def launch_count(self) -> int:

@@ -23,6 +23,7 @@
 #pragma once
 
 #include "kernels.cuh"
+#include "spmv_sym.cuh"
 
 namespace macroc {
 
@@ -139,34 +140,75 @@ k_gather_forces(GridDev g, ElemRange er, int l0, int nl, int k0, int nk, const d
     if (threadIdx.x == 0) partial[blockIdx.x] = s;
 }
 
-// General Jacobian assembly, one CTA (8 warps) per operator tile.
-template <bool PER_GP>
-__global__ void __launch_bounds__(256)
-k_assemble_elements(GridDev g, ElemRange er, double wg, const double *__restrict__ ctan_gp,
-                    const uint8_t *__restrict__ nodemask, double2 *__restrict__ A, double *__restrict__ dinv)
+// kk = slot*9 + 3*row + col  ->  slot | row << 5 | col << 7 | diagonal << 9   (entry 243 is padding)
+struct KkInfo {
+    unsigned short v[244];
+};
+constexpr KkInfo make_kkinfo()
+{
+    KkInfo t{};
+    for (int kk = 0; kk < 243; ++kk) {
+        const int slot = kk / 9, rr = (kk % 9) / 3, cc = kk % 3;
+        t.v[kk] = (unsigned short)(slot | (rr << 5) | (cc << 7) | ((slot == 13 && rr == cc) ? 1 << 9 : 0));
+    }
+    t.v[243] = 0x8000;
+    return t;
+}
+__constant__ KkInfo c_kkinfo = make_kkinfo();
+
+// General Jacobian assembly (assembly.c:85-108 with a tangent per Gauss point), one CTA of 8 warps
+// per operator tile: warp a = local node a of the element, lane = node.  SYM: the tile is a row
+// tile of the symmetric layout (spmv_sym.cuh) and only the slots 13..26 are stored -- the tangent
+// must then be symmetric (Ke is; the reference never relies on it, MATAIJ stores both halves).
+// The Gauss-point loop is fully unrolled so that every shape-function derivative of the block
+// columns is an immediate constant-bank operand of its DFMA; wg is applied once, when a thread adds
+// its 3 x 24 row block to the tile.
+template <bool PER_GP, bool SYM>
+__global__ void __launch_bounds__(256, 1)
+k_assemble_elements(GridDev g, SymGeom sg, ElemRange er, double wg, const double *__restrict__ ctan_gp,
+                    const uint8_t *__restrict__ nodemask, double2 *__restrict__ A, double *__restrict__ dinv,
+                    int64_t tile_lo, int64_t tile_hi)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double *tileA = reinterpret_cast<double *>(smem_raw);                  // TILE_DOUBLES
+    double *tileA = reinterpret_cast<double *>(smem_raw);                  // TILE_DOUBLES, full 27-slot indexing
     uint8_t *nbmask = smem_raw + TILE_DOUBLES * sizeof(double);            // [27][32]
     const int lane = threadIdx.x & 31, a = threadIdx.x >> 5;
     const int apx = node_px(a), apy = node_py(a), apz = node_pz(a);
     const int64_t per_layer = er.nex * er.ney;
 
-    for (int64_t tile = blockIdx.x; tile < g.ntiles; tile += gridDim.x) {
-        const int64_t ln = tile * TILE_NODES + lane;
-        const bool valid = ln < g.nloc;
-        int i = 0, j = 0, k = 0;
-        if (valid) { i = (int)(ln % g.NX); j = (int)((ln / g.NX) % g.NY); k = (int)(ln / g.npl) + g.zs; }
+    for (int64_t tile = tile_lo + blockIdx.x; tile < tile_hi; tile += gridDim.x) {
+        // node of (tile, lane): local box coordinates (i, j), slab-local plane kl, linear index ln0 of lane 0
+        int i = 0, j = 0, kl = 0, nvalid = 0;
+        int64_t ln0;
+        if (SYM) {
+            const int64_t tpp = sym_tiles_per_plane(g, sg);
+            kl = (int)((tile + tpp) / tpp) - 1;                            // floor: the ghost plane is -1
+            const int64_t rem = tile - (int64_t)kl * tpp;
+            j = (int)(rem / sg.rt);
+            const int x0 = (int)(rem % sg.rt) * 32;
+            i = x0 + lane;
+            nvalid = min(32, g.NX - x0);
+            ln0 = x0 + (int64_t)g.NX * j + g.npl * kl;
+        } else {
+            ln0 = tile * TILE_NODES;
+            const int64_t ln = ln0 + lane;
+            nvalid = (int)min((int64_t)32, g.nloc - ln0);
+            if (lane < nvalid) { i = (int)(ln % g.NX); j = (int)((ln / g.NX) % g.NY); kl = (int)(ln / g.npl); }
+        }
+        const bool valid = lane < nvalid;
+        const int k = kl + g.zs;
         for (int q = threadIdx.x; q < TILE_DOUBLES; q += blockDim.x) tileA[q] = 0.;
         for (int q = threadIdx.x; q < 27 * 32; q += blockDim.x) {
-            int slot = q >> 5, l2 = q & 31;
-            int64_t ln2 = tile * TILE_NODES + l2;
+            const int slot = q >> 5, l2 = q & 31;
             const int ddx = slot % 3 - 1, ddy = (slot / 3) % 3 - 1, ddz = slot / 9 - 1;
-            nbmask[q] = ln2 < g.nloc ? nodemask[g.G + ln2 + ddx + (int64_t)g.NX * ddy + g.npl * ddz] : 0;
+            // (the ghost plane of the symmetric layout would look two planes below the slab)
+            const int64_t idx = g.G + ln0 + l2 + ddx + (int64_t)g.NX * ddy + g.npl * ddz;
+            nbmask[q] = (l2 < nvalid && idx >= 0 && idx < g.S) ? nodemask[idx] : 0;
         }
-        // the element in which this node is local node a
+        // the element in which this node is local node a (it must be one whose tangents this rank holds)
         const int ei = i - apx, ej = j - apy, ek = k - apz;
-        const bool exists = valid && ei >= 0 && ei < g.NX - 1 && ej >= 0 && ej < g.NY - 1 && ek >= 0 && ek < g.NZ - 1;
+        const bool exists = valid && ei >= 0 && ei < g.NX - 1 && ej >= 0 && ej < g.NY - 1 && ek >= 0 && ek < g.NZ - 1 &&
+                            ek >= er.ezs && ek < er.ezs + er.nez_ext;
         double blk[3][24];
 #pragma unroll
         for (int d = 0; d < 3; ++d)
@@ -174,35 +216,38 @@ k_assemble_elements(GridDev g, ElemRange er, double wg, const double *__restrict
             for (int q = 0; q < 24; ++q) blk[d][q] = 0.;
         if (exists) {
             const double *cg = PER_GP ? ctan_gp + ((int64_t)(ek - er.ezs) * per_layer + ei + er.nex * (int64_t)ej) : nullptr;
-#pragma unroll 1
+            // uniform tangent: fully unrolled (every B entry an immediate operand).  Per-Gauss-point
+            // tangents: one Gauss point per loop trip -- unrolled, the 288 loads of a thread serialise
+            // behind the register allocator (measured 84 ms against 67 ms at 256^3)
+#pragma unroll (PER_GP ? 1 : 8)
             for (int gp = 0; gp < 8; ++gp) {
                 const double hx = c_dsh[gp][a][0], hy = c_dsh[gp][a][1], hz = c_dsh[gp][a][2];
-                // stream the tangent one column k at a time: T[d] = (B_a^T C)[d][k] * wg, then every
-                // block column b takes T[d] * B_b[k][.]  (B has at most two non-zeros per (k, b))
+                // stream the tangent one column k at a time: T[d] = (B_a^T C)[d][k], then every block
+                // column b takes T[d] * B_b[k][.]  (B has at most two non-zeros per (k, b))
 #pragma unroll
-                for (int k = 0; k < 6; ++k) {
+                for (int kc = 0; kc < 6; ++kc) {
                     double ck[6];
 #pragma unroll
-                    for (int r = 0; r < 6; ++r) ck[r] = PER_GP ? __ldg(cg + (int64_t)(gp * 36 + r * 6 + k) * er.ne_ext) : c_D[r * 6 + k];
-                    const double T0 = (hx * ck[0] + hy * ck[3] + hz * ck[4]) * wg;
-                    const double T1 = (hy * ck[1] + hx * ck[3] + hz * ck[5]) * wg;
-                    const double T2 = (hz * ck[2] + hx * ck[4] + hy * ck[5]) * wg;
+                    for (int r = 0; r < 6; ++r) ck[r] = PER_GP ? __ldg(cg + (int64_t)(gp * 36 + r * 6 + kc) * er.ne_ext) : c_D[r * 6 + kc];
+                    const double T0 = fma(hz, ck[4], fma(hy, ck[3], hx * ck[0]));
+                    const double T1 = fma(hz, ck[5], fma(hx, ck[3], hy * ck[1]));
+                    const double T2 = fma(hy, ck[5], fma(hx, ck[4], hz * ck[2]));
 #pragma unroll
                     for (int b = 0; b < 8; ++b) {
                         const double bx = c_dsh[gp][b][0], by = c_dsh[gp][b][1], bz = c_dsh[gp][b][2];
                         // column 3b+c of B: row k non-zero for (k,c) in {(0,0),(1,1),(2,2),(3,0)=by,(3,1)=bx,(4,0)=bz,(4,2)=bx,(5,1)=bz,(5,2)=by}
-                        if (k == 0) { blk[0][3 * b + 0] = fma(T0, bx, blk[0][3 * b + 0]); blk[1][3 * b + 0] = fma(T1, bx, blk[1][3 * b + 0]); blk[2][3 * b + 0] = fma(T2, bx, blk[2][3 * b + 0]); }
-                        if (k == 1) { blk[0][3 * b + 1] = fma(T0, by, blk[0][3 * b + 1]); blk[1][3 * b + 1] = fma(T1, by, blk[1][3 * b + 1]); blk[2][3 * b + 1] = fma(T2, by, blk[2][3 * b + 1]); }
-                        if (k == 2) { blk[0][3 * b + 2] = fma(T0, bz, blk[0][3 * b + 2]); blk[1][3 * b + 2] = fma(T1, bz, blk[1][3 * b + 2]); blk[2][3 * b + 2] = fma(T2, bz, blk[2][3 * b + 2]); }
-                        if (k == 3) {
+                        if (kc == 0) { blk[0][3 * b + 0] = fma(T0, bx, blk[0][3 * b + 0]); blk[1][3 * b + 0] = fma(T1, bx, blk[1][3 * b + 0]); blk[2][3 * b + 0] = fma(T2, bx, blk[2][3 * b + 0]); }
+                        if (kc == 1) { blk[0][3 * b + 1] = fma(T0, by, blk[0][3 * b + 1]); blk[1][3 * b + 1] = fma(T1, by, blk[1][3 * b + 1]); blk[2][3 * b + 1] = fma(T2, by, blk[2][3 * b + 1]); }
+                        if (kc == 2) { blk[0][3 * b + 2] = fma(T0, bz, blk[0][3 * b + 2]); blk[1][3 * b + 2] = fma(T1, bz, blk[1][3 * b + 2]); blk[2][3 * b + 2] = fma(T2, bz, blk[2][3 * b + 2]); }
+                        if (kc == 3) {
                             blk[0][3 * b + 0] = fma(T0, by, blk[0][3 * b + 0]); blk[1][3 * b + 0] = fma(T1, by, blk[1][3 * b + 0]); blk[2][3 * b + 0] = fma(T2, by, blk[2][3 * b + 0]);
                             blk[0][3 * b + 1] = fma(T0, bx, blk[0][3 * b + 1]); blk[1][3 * b + 1] = fma(T1, bx, blk[1][3 * b + 1]); blk[2][3 * b + 1] = fma(T2, bx, blk[2][3 * b + 1]);
                         }
-                        if (k == 4) {
+                        if (kc == 4) {
                             blk[0][3 * b + 0] = fma(T0, bz, blk[0][3 * b + 0]); blk[1][3 * b + 0] = fma(T1, bz, blk[1][3 * b + 0]); blk[2][3 * b + 0] = fma(T2, bz, blk[2][3 * b + 0]);
                             blk[0][3 * b + 2] = fma(T0, bx, blk[0][3 * b + 2]); blk[1][3 * b + 2] = fma(T1, bx, blk[1][3 * b + 2]); blk[2][3 * b + 2] = fma(T2, bx, blk[2][3 * b + 2]);
                         }
-                        if (k == 5) {
+                        if (kc == 5) {
                             blk[0][3 * b + 1] = fma(T0, bz, blk[0][3 * b + 1]); blk[1][3 * b + 1] = fma(T1, bz, blk[1][3 * b + 1]); blk[2][3 * b + 1] = fma(T2, bz, blk[2][3 * b + 1]);
                             blk[0][3 * b + 2] = fma(T0, by, blk[0][3 * b + 2]); blk[1][3 * b + 2] = fma(T1, by, blk[1][3 * b + 2]); blk[2][3 * b + 2] = fma(T2, by, blk[2][3 * b + 2]);
                         }
@@ -222,32 +267,39 @@ k_assemble_elements(GridDev g, ElemRange er, double wg, const double *__restrict
 #pragma unroll
                     for (int cc = 0; cc < 3; ++cc) {
                         const int kk = slot * 9 + 3 * d + cc;
-                        tileA[((kk >> 1) * TILE_NODES + lane) * 2 + (kk & 1)] += blk[d][3 * b + cc];
+                        double *cell = tileA + ((kk >> 1) * TILE_NODES + lane) * 2 + (kk & 1);
+                        *cell = fma(blk[d][3 * b + cc], wg, *cell);
                     }
             }
             __syncthreads();
         }
-        // MatZeroRowsColumns (bcs.c:341-347) + PCJACOBI diagonal + coalesced store
-        double2 *At = A + tile * (PAIRS * TILE_NODES);
-        for (int q = threadIdx.x; q < PAIRS * TILE_NODES; q += blockDim.x) {
-            const int l2 = q & 31, pr = q >> 5;
-            const unsigned own = nbmask[13 * 32 + l2];
-            double v2[2];
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int kk = 2 * pr + h;
-                double v = tileA[2 * q + h];
-                if (kk < ENTRIES) {
-                    const int slot = kk / 9, rr = (kk % 9) / 3, cc = kk % 3;
-                    const unsigned nb = nbmask[slot * 32 + l2];
-                    if (((own >> rr) & 1u) || ((nb >> cc) & 1u)) v = (slot == 13 && rr == cc) ? 1. : 0.;
-                    if (slot == 13 && rr == cc && tile * TILE_NODES + l2 < g.nloc)
-                        dinv[rr * g.S + g.G + tile * TILE_NODES + l2] = v != 0. ? 1. / v : 1.;
-                } else
-                    v = 0.;
-                v2[h] = v;
+        // MatZeroRowsColumns (bcs.c:341-347) + PCJACOBI diagonal + coalesced store; warp a takes the
+        // entry pairs a, a+8, ...: the entry decoding (slot, row, col) is a warp-uniform table lookup
+        const unsigned own = nbmask[13 * 32 + lane];
+        auto masked = [&](int kk) -> double {
+            const unsigned info = c_kkinfo.v[kk];
+            if (info & 0x8000u) return 0.;
+            const int slot = info & 31, rr = (info >> 5) & 3, cc = (info >> 7) & 3;
+            double v = tileA[((kk >> 1) * TILE_NODES + lane) * 2 + (kk & 1)];
+            const unsigned nb = nbmask[slot * 32 + lane];
+            const bool isdiag = (info >> 9) & 1u;
+            if (((own >> rr) & 1u) || ((nb >> cc) & 1u)) v = isdiag ? 1. : 0.;
+            if (SYM && kl < 0 && slot < 18) v = 0.;                  // ghost plane: only the blocks towards the slab
+            if (isdiag && valid && (!SYM || kl >= 0)) dinv[rr * g.S + g.G + ln0 + lane] = v != 0. ? 1. / v : 1.;
+            return v;
+        };
+        if (SYM) {
+            double2 *At = A + tile * (SYM_PAIRS * TILE_NODES) + lane;
+            for (int pr = a; pr < SYM_PAIRS; pr += 8) {
+                const double v0 = masked(117 + 2 * pr), v1 = masked(118 + 2 * pr);
+                At[pr * TILE_NODES] = make_double2(v0, v1);
             }
-            At[q] = make_double2(v2[0], v2[1]);
+        } else {
+            double2 *At = A + tile * (PAIRS * TILE_NODES) + lane;
+            for (int pr = a; pr < PAIRS; pr += 8) {
+                const double v0 = masked(2 * pr), v1 = masked(2 * pr + 1);
+                At[pr * TILE_NODES] = make_double2(v0, v1);
+            }
         }
         __syncthreads();
     }

@@ -47,8 +47,9 @@ struct macroc_ctx {
     double *vec[V_COUNT] = {nullptr};
     double2 *A = nullptr;
     double2 *Asym = nullptr;         // symmetric storage (14 of 27 slots), MACROC_OP_ASSEMBLED_SYM; points at tile 0
-    double2 *Asym_alloc = nullptr;   // start of the allocation: Asym_front tiles of the ghost plane below, then the slab
-    int64_t Asym_front = 0;
+    double2 *Asym_alloc = nullptr;   // start of the allocation: the ghost plane below (if any), then the slab
+    SymGeom sg = {1, 0};
+    int sym_R = 0, sym_nseg = 0, sym_variant = 0, sym_hint = 0;   // tuning overrides (MACROC_SYM_R / _NSEG / _VARIANT / _HINT, read once at create)
     bool A_valid = false, mf_ready = false, Asym_valid = false;
     double *Ke = nullptr, *T = nullptr;
     uint8_t *nodemask = nullptr, *ghostflag = nullptr;
@@ -90,6 +91,8 @@ struct macroc_ctx {
     int prof_stride = 1, prof_used = 0;
     int64_t prof_counter = 0, prof_samples = 0;
     double prof_ms = 0.;
+    double prof_solve_ms = 0.;       // device time of the PCG solves while the profile is on
+    int64_t prof_solve_its = 0;
     std::string err;
 };
 
@@ -381,8 +384,8 @@ extern "C" int macroc_create(const macroc_config *cfg, int rank, int nranks, con
         FAIL((macroc_ctx *)nullptr, MACROC_ERR_ARG, "macroc_create: unknown jac_mode %d", (int)cfg->jac_mode);
     if (cfg->ksp_maxits < 0 || cfg->newton_max_its < 0)
         FAIL((macroc_ctx *)nullptr, MACROC_ERR_ARG, "macroc_create: negative iteration limit");
-    if (cfg->material == MACROC_MAT_PER_GP && cfg->op != MACROC_OP_ASSEMBLED)
-        FAIL((macroc_ctx *)nullptr, MACROC_ERR_UNSUPPORTED, "macroc_create: per-Gauss-point tangents need the assembled operator");
+    if (cfg->material == MACROC_MAT_PER_GP && cfg->op == MACROC_OP_MATRIX_FREE)
+        FAIL((macroc_ctx *)nullptr, MACROC_ERR_UNSUPPORTED, "macroc_create: per-Gauss-point tangents need an assembled operator");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
         cudaGetLastError();
@@ -392,6 +395,10 @@ extern "C" int macroc_create(const macroc_config *cfg, int rank, int nranks, con
     c->id = g_next_ctx_id++;
     c->cfg = *cfg; c->slab = slab; c->geo = make_geometry(*cfg);
     if (const char *v = getenv("MACROC_SPMV_VARIANT")) c->spmv_variant = atoi(v);
+    if (const char *v = getenv("MACROC_SYM_R")) c->sym_R = atoi(v);
+    if (const char *v = getenv("MACROC_SYM_NSEG")) c->sym_nseg = atoi(v);
+    if (const char *v = getenv("MACROC_SYM_VARIANT")) c->sym_variant = atoi(v);
+    if (const char *v = getenv("MACROC_SYM_HINT")) c->sym_hint = atoi(v);
     if (cfg->device >= 0) c->device = cfg->device;
     else if (cudaGetDevice(&c->device) != cudaSuccess) c->device = 0;
 #define CUC(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { g_last_error = std::string(#call) + " -> " + cudaGetErrorString(_e); ctx_free(c); return MACROC_ERR_CUDA; } } while (0)
@@ -407,6 +414,8 @@ extern "C" int macroc_create(const macroc_config *cfg, int rank, int nranks, con
     g.npl = slab.npl; g.nloc = slab.nloc;
     g.Xs = slab.Xs; g.Ys = slab.Ys; g.ox0 = slab.xs - slab.Xs; g.oy0 = slab.ys - slab.Ys; g.xm = slab.xm; g.ym = slab.ym;
     g.ghost = nullptr;
+    c->sg.rt = (slab.NX + TILE_NODES - 1) / TILE_NODES;
+    c->sg.zmin = slab.has_lower() ? -1 : 0;
     g.G = (int)(((slab.npl + slab.NX + 1 + 31) / 32) * 32);
     g.ntiles = (slab.nloc + TILE_NODES - 1) / TILE_NODES;
     g.S = g.ntiles * TILE_NODES + 2 * (int64_t)g.G + 32;
@@ -890,12 +899,21 @@ static int ensure_operator_storage(macroc_ctx *c)
     return MACROC_OK;
 }
 
-// Symmetric storage: uniform tangent only.  Several ranks (ghost-plane copy in front of tile 0) are
-// implemented but have not run on hardware yet: opt in with MACROC_SYM_MULTIRANK=1.
-static int sym_supported(macroc_ctx *c)
+// Launch of the per-element Jacobian kernel into the full (27-slot) or the symmetric (14-slot) layout.
+template <bool SYM>
+static int launch_assemble_elements(macroc_ctx *c, bool per_gp, double2 *A, int64_t tile_lo, int64_t tile_hi)
 {
-    if (c->cfg.material != MACROC_MAT_UNIFORM)
-        FAIL(c, MACROC_ERR_UNSUPPORTED, "symmetric operator storage needs the uniform tangent");
+    const int smem = TILE_DOUBLES * (int)sizeof(double) + 27 * 32;
+    static bool configured[64] = {false};                     // function attributes are per device
+    if (!configured[c->device & 63]) {
+        CU(c, cudaFuncSetAttribute(k_assemble_elements<true, SYM>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CU(c, cudaFuncSetAttribute(k_assemble_elements<false, SYM>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured[c->device & 63] = true;
+    }
+    const int blocks = (int)std::min<int64_t>(tile_hi - tile_lo, 148 * 3);
+    if (per_gp) k_assemble_elements<true, SYM><<<blocks, 256, smem, c->stream>>>(c->g, c->sg, c->er, c->geo.wg, c->ctan, c->nodemask, A, c->vec[V_DINV], tile_lo, tile_hi);
+    else k_assemble_elements<false, SYM><<<blocks, 256, smem, c->stream>>>(c->g, c->sg, c->er, c->geo.wg, c->ctan, c->nodemask, A, c->vec[V_DINV], tile_lo, tile_hi);
+    c->launches++;
     return MACROC_OK;
 }
 
@@ -905,18 +923,28 @@ extern "C" int macroc_assembly_jac(macroc_ctx *c)
     CU(c, cudaSetDevice(c->device));
     BIND_CONSTANTS(c);
     if (c->cfg.op == MACROC_OP_ASSEMBLED_SYM) {
-        int rc = sym_supported(c);
-        if (rc) return rc;
+        const int64_t tpp = sym_tiles_per_plane(c->g, c->sg);
+        const int64_t tile_lo = c->sg.zmin * tpp, tile_hi = tpp * c->g.nzl;
         if (!c->Asym_alloc) {
-            // a lower z neighbour: keep a private copy of the ghost plane's dz = +1 blocks in front of tile 0
-            c->Asym_front = c->slab.has_lower() ? (c->g.npl + TILE_NODES - 1) / TILE_NODES : 0;
-            size_t bytes = (size_t)SYM_TILE_BYTES * (size_t)(c->g.ntiles + c->Asym_front);
+            // with a lower z neighbour the ghost plane's dz = +1 blocks are kept as a private copy (plane -1)
+            size_t bytes = (size_t)SYM_TILE_BYTES * (size_t)(tile_hi - tile_lo);
             cudaError_t e = cudaMalloc(&c->Asym_alloc, bytes);
             if (e != cudaSuccess) { cudaGetLastError(); FAIL(c, MACROC_ERR_MEM, "operator needs %.2f GB of device memory", bytes / 1e9); }
-            c->Asym = c->Asym_alloc + c->Asym_front * (int64_t)(SYM_PAIRS * TILE_NODES);
+            c->Asym = c->Asym_alloc - tile_lo * (int64_t)(SYM_PAIRS * TILE_NODES);
         }
-        LAUNCH(c, k_fill_operator_sym, cdiv64(c->g.ntiles + c->Asym_front, 8), 256, c->g, c->T, c->nodemask, c->Asym, c->vec[V_DINV],
-               -c->Asym_front);
+        const bool per_gp = c->cfg.material == MACROC_MAT_PER_GP;
+        if (per_gp || c->cfg.jac_mode == MACROC_JAC_ELEMENT) {
+            // per-Gauss-point tangents (assumed symmetric, like Ke itself): the element kernel writes slots 13..26
+            if (per_gp) {
+                if (!c->ctan) FAIL(c, MACROC_ERR_ARG, "assembly_jac: no Gauss-point tangents (call homogenize)");
+                int rc = halo_gp_layer(c, c->ctan, 288);   // 8 gp x 36
+                if (rc) return rc;
+            }
+            int rc = launch_assemble_elements<true>(c, per_gp, c->Asym, tile_lo, tile_hi);
+            if (rc) return rc;
+        } else
+            LAUNCH(c, k_fill_operator_sym, cdiv64(tile_hi - tile_lo, 8), 256, c->g, c->sg, c->T, c->nodemask, c->Asym, c->vec[V_DINV],
+                   tile_lo, tile_hi);
         c->Asym_valid = true;
     } else if (c->cfg.op == MACROC_OP_MATRIX_FREE) {
         if (c->cfg.material != MACROC_MAT_UNIFORM) FAIL(c, MACROC_ERR_UNSUPPORTED, "matrix-free operator needs the uniform tangent");
@@ -931,17 +959,7 @@ extern "C" int macroc_assembly_jac(macroc_ctx *c)
                 if (!c->ctan) FAIL(c, MACROC_ERR_ARG, "assembly_jac: no Gauss-point tangents (call homogenize)");
                 if ((rc = halo_gp_layer(c, c->ctan, 288))) return rc;   // 8 gp x 36
             }
-            const int smem = TILE_DOUBLES * (int)sizeof(double) + 27 * 32;
-            static bool configured[64] = {false};
-            if (!configured[c->device & 63]) {
-                cudaFuncSetAttribute(k_assemble_elements<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-                cudaFuncSetAttribute(k_assemble_elements<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-                configured[c->device & 63] = true;
-            }
-            int blocks = (int)std::min<int64_t>(c->g.ntiles, 148 * 3);
-            if (per_gp) k_assemble_elements<true><<<blocks, 256, smem, c->stream>>>(c->g, c->er, c->geo.wg, c->ctan, c->nodemask, c->A, c->vec[V_DINV]);
-            else k_assemble_elements<false><<<blocks, 256, smem, c->stream>>>(c->g, c->er, c->geo.wg, c->ctan, c->nodemask, c->A, c->vec[V_DINV]);
-            c->launches++;
+            if ((rc = launch_assemble_elements<false>(c, per_gp, c->A, 0, c->g.ntiles))) return rc;
         } else
             LAUNCH(c, k_fill_operator, cdiv64(c->g.ntiles, 8), 256, c->g, c->T, c->nodemask, c->A, c->vec[V_DINV]);
         c->A_valid = true;
@@ -987,6 +1005,36 @@ static int spmv_launch(macroc_ctx *c, double *p, double *w, int64_t first, int64
     }
 }
 
+// symmetric-storage SpMV over the owned planes [first, first + count): bands of R rows x z
+// segments, about one item per resident warp.  Returns the number of partials written (< 0: error).
+template <int WARPS, int NSTAGE, int RMAX>
+static int spmv_sym_launch(macroc_ctx *c, double *p, double *w, int first, int count, double *partial, bool with_dot,
+                           const int *done)
+{
+    using SM = SpmvSymSmem<WARPS, NSTAGE, RMAX>;
+    const GridDev &g = c->g;
+    static bool configured[64] = {false};          // function attributes are per device
+    if (!configured[c->device & 63]) {
+        cudaError_t e1 = cudaFuncSetAttribute(k_spmv_sym<WARPS, NSTAGE, RMAX, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::total);
+        cudaError_t e2 = cudaFuncSetAttribute(k_spmv_sym<WARPS, NSTAGE, RMAX, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::total);
+        if (e1 != cudaSuccess || e2 != cudaSuccess) return -1;
+        configured[c->device & 63] = true;
+    }
+    const int64_t target = (int64_t)148 * WARPS;
+    int R = c->sym_R > 0 ? c->sym_R : (int)std::min<int64_t>(RMAX, std::max<int64_t>(1, (int64_t)c->sg.rt * g.NY * count / target));
+    R = std::max(1, std::min({R, RMAX, g.NY}));
+    const int64_t bands = (int64_t)c->sg.rt * ((g.NY + R - 1) / R);
+    int nseg = c->sym_nseg > 0 ? c->sym_nseg : (int)std::max<int64_t>(1, target / bands);
+    nseg = std::min(nseg, count);
+    const int lseg = (count + nseg - 1) / nseg;
+    nseg = (count + lseg - 1) / lseg;                 // drop empty segments
+    const int blocks = (int)std::min<int64_t>(cdiv64(bands * nseg, WARPS), 148);
+    if (with_dot) k_spmv_sym<WARPS, NSTAGE, RMAX, true><<<blocks, WARPS * 32, SM::total, c->stream>>>(g, c->sg, c->Asym, p, w, first, first + count, R, nseg, partial, done, c->sym_hint);
+    else k_spmv_sym<WARPS, NSTAGE, RMAX, false><<<blocks, WARPS * 32, SM::total, c->stream>>>(g, c->sg, c->Asym, p, w, first, first + count, R, nseg, partial, done, c->sym_hint);
+    c->launches++;
+    return blocks;
+}
+
 // w = A p on the context's stream; p's halo is exchanged on comm_stream while
 // the rows that do not touch a ghost plane are computed.
 static int apply_operator(macroc_ctx *c, int op, double *p, double *w, bool with_dot, const int *done,
@@ -995,11 +1043,15 @@ static int apply_operator(macroc_ctx *c, int op, double *p, double *w, bool with
     const GridDev &g = c->g;
     const bool comm = has_comm(c);
     const bool mf = op == MACROC_OP_MATRIX_FREE;
-    int64_t lo_end = 0, hi_begin = mf ? g.nloc : g.ntiles;     // interior range in nodes (mf) or tiles
+    const bool symop = op == MACROC_OP_ASSEMBLED_SYM;
+    // interior range in nodes (matrix-free), planes (symmetric storage) or tiles (full storage)
+    const int64_t total = mf ? g.nloc : (symop ? (int64_t)g.nzl : g.ntiles);
+    int64_t lo_end = 0, hi_begin = total;
     if (comm && g.nzl >= 3) {
         if (mf) { lo_end = g.npl; hi_begin = g.nloc - g.npl; }
+        else if (symop) { lo_end = 1; hi_begin = g.nzl - 1; }
         else { lo_end = (g.npl + TILE_NODES - 1) / TILE_NODES; hi_begin = (g.nloc - g.npl) / TILE_NODES; }
-        if (hi_begin <= lo_end) { lo_end = 0; hi_begin = mf ? g.nloc : g.ntiles; }
+        if (hi_begin <= lo_end) { lo_end = 0; hi_begin = total; }
     }
     const bool split = comm && lo_end > 0;
     if (comm) {
@@ -1017,38 +1069,23 @@ static int apply_operator(macroc_ctx *c, int op, double *p, double *w, bool with
             if (rc) return rc;
         }
     }
-    int nparts = 0;
+    int nparts = 0, rc_run = MACROC_OK;
     auto run = [&](int64_t first, int64_t count) {
         if (count <= 0) return;
         int blocks;
-        if (op == MACROC_OP_ASSEMBLED_SYM) {
-            const int64_t tpp = (g.npl + TILE_NODES - 1) / TILE_NODES, rt = (g.NX + TILE_NODES - 1) / TILE_NODES;
-            static const int sym_variant = getenv("MACROC_SYM_VARIANT") ? atoi(getenv("MACROC_SYM_VARIANT")) : 0;
-            static const int sym_hint = getenv("MACROC_SYM_HINT") ? atoi(getenv("MACROC_SYM_HINT")) : 1;
-            static const int sym_nseg = getenv("MACROC_SYM_NSEG") ? atoi(getenv("MACROC_SYM_NSEG")) : 0;
-            const int64_t mtot = (g.ntiles + tpp - 1) / tpp;
-            auto go = [&](auto kern_dot, auto kern_nodot, int warps, int ns, int per_sm) {
-                const int64_t pencils = rt * ((((tpp + rt - 1) / rt) + warps - 1) / warps);
-                int nseg = sym_nseg > 0 ? sym_nseg : (int)std::max<int64_t>(1, (148 * 7 + pencils - 1) / pencils);
-                nseg = (int)std::min<int64_t>(nseg, std::max<int64_t>(1, mtot / 8));     // segments of >= 8 planes
-                const int smem = warps * ns * CHUNK_BYTES + warps * ns * 8 + warps * 8;
-                static bool configured[64] = {false};          // function attributes are per device (one variant per process)
-                if (!configured[c->device & 63]) {
-                    cudaFuncSetAttribute(kern_dot, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-                    cudaFuncSetAttribute(kern_nodot, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-                    configured[c->device & 63] = true;
-                }
-                blocks = (int)std::min<int64_t>(pencils * nseg, (int64_t)148 * per_sm);
-                if (with_dot) kern_dot<<<blocks, warps * 32, smem, c->stream>>>(g, c->Asym, p, w, first, count, tpp, rt, nseg, c->partial + nparts, done, -c->Asym_front * TILE_NODES, sym_hint);
-                else kern_nodot<<<blocks, warps * 32, smem, c->stream>>>(g, c->Asym, p, w, first, count, tpp, rt, nseg, c->partial + nparts, done, -c->Asym_front * TILE_NODES, sym_hint);
-                c->launches++;
-            };
-            if (sym_variant == 1) go(k_spmv_sym<8, 2, 2, true>, k_spmv_sym<8, 2, 2, false>, 8, 2, 2);
-            else if (sym_variant == 2) go(k_spmv_sym<8, 3, 1, true>, k_spmv_sym<8, 3, 1, false>, 8, 3, 1);
-            else if (sym_variant == 3) go(k_spmv_sym<4, 7, 1, true>, k_spmv_sym<4, 7, 1, false>, 4, 7, 1);
-            else if (sym_variant == 4) go(k_spmv_sym<6, 5, 1, true>, k_spmv_sym<6, 5, 1, false>, 6, 5, 1);
-            else if (sym_variant == 5) go(k_spmv_sym<4, 4, 2, true>, k_spmv_sym<4, 4, 2, false>, 4, 4, 2);
-            else go(k_spmv_sym<8, 4, 1, true>, k_spmv_sym<8, 4, 1, false>, 8, 4, 1);
+        if (symop) {
+            // planes [first, first + count)
+            switch (c->sym_variant) {
+                case 1: blocks = spmv_sym_launch<8, 3, 6>(c, p, w, (int)first, (int)count, c->partial + nparts, with_dot, done); break;
+                case 2: blocks = spmv_sym_launch<8, 4, 4>(c, p, w, (int)first, (int)count, c->partial + nparts, with_dot, done); break;
+                case 3: blocks = spmv_sym_launch<8, 2, 16>(c, p, w, (int)first, (int)count, c->partial + nparts, with_dot, done); break;
+                case 4: blocks = spmv_sym_launch<6, 4, 10>(c, p, w, (int)first, (int)count, c->partial + nparts, with_dot, done); break;
+                case 5: blocks = spmv_sym_launch<8, 3, 10>(c, p, w, (int)first, (int)count, c->partial + nparts, with_dot, done); break;
+                case 6: blocks = spmv_sym_launch<4, 6, 32>(c, p, w, (int)first, (int)count, c->partial + nparts, with_dot, done); break;
+                case 7: blocks = spmv_sym_launch<4, 5, 32>(c, p, w, (int)first, (int)count, c->partial + nparts, with_dot, done); break;
+                default: blocks = spmv_sym_launch<8, 3, 16>(c, p, w, (int)first, (int)count, c->partial + nparts, with_dot, done); break;
+            }
+            if (blocks < 0) { rc_run = MACROC_ERR_CUDA; return; }
         } else if (mf) {
             // node ranges are whole planes here
             const int k0 = (int)(first / g.npl), k1 = (int)((first + count) / g.npl);
@@ -1071,7 +1108,6 @@ static int apply_operator(macroc_ctx *c, int op, double *p, double *w, bool with
         }
         nparts += blocks;
     };
-    const int64_t total = mf ? g.nloc : g.ntiles;
     if (split) {
         run(lo_end, hi_begin - lo_end);
         CU(c, cudaStreamWaitEvent(c->stream, c->ev_halo, 0));
@@ -1079,6 +1115,7 @@ static int apply_operator(macroc_ctx *c, int op, double *p, double *w, bool with
         run(hi_begin, total - hi_begin);
     } else
         run(0, total);
+    if (rc_run) FAIL(c, rc_run, "apply_operator: kernel configuration failed (shared memory)");
     if (with_dot) {
         if (fuse_pw_scalars) LAUNCH(c, k_cg_reduce_pw, 1, 256, c->partial, nparts, c->sc);
         else LAUNCH(c, k_reduce, 1, 256, c->partial, nparts, c->sums);
@@ -1141,6 +1178,7 @@ extern "C" int macroc_solve_Ax(macroc_ctx *c, int *its, double *rnorm)
     if (op == MACROC_OP_ASSEMBLED && !c->A_valid) FAIL(c, MACROC_ERR_ARG, "solve_Ax: assembly_jac has not been called");
     if (op == MACROC_OP_ASSEMBLED_SYM && !c->Asym_valid) FAIL(c, MACROC_ERR_ARG, "solve_Ax: assembly_jac has not been called");
     if (op == MACROC_OP_MATRIX_FREE && !c->mf_ready) FAIL(c, MACROC_ERR_ARG, "solve_Ax: assembly_jac has not been called");
+    if (c->prof_on) CU(c, cudaEventRecord(c->ev_t0, c->stream));
     int rc = cg_begin(c, c->cfg.ksp_rtol, c->cfg.ksp_abstol, c->cfg.ksp_dtol, c->cfg.ksp_maxits);
     if (rc) return rc;
     // The iteration count lives on the device; the host only polls a "done"
@@ -1187,8 +1225,12 @@ extern "C" int macroc_solve_Ax(macroc_ctx *c, int *its, double *rnorm)
         }
     }
     CU(c, cudaMemcpyAsync(&c->sc_host[0], c->sc, sizeof(CgScalars), cudaMemcpyDeviceToHost, c->stream));
+    if (c->prof_on) CU(c, cudaEventRecord(c->ev_t1, c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
     if (c->prof_on) {
+        float sms = 0.f;
+        CU(c, cudaEventElapsedTime(&sms, c->ev_t0, c->ev_t1));
+        c->prof_solve_ms += sms; c->prof_solve_its += c->sc_host[0].its;
         // samples taken after convergence bracket no-op launches: keep the first `its` only
         int64_t stride = c->prof_stride;
         for (int q = 0; q < c->prof_used; ++q) {
@@ -1208,7 +1250,6 @@ extern "C" int macroc_solve_Ax(macroc_ctx *c, int *its, double *rnorm)
 extern "C" int macroc_set_operator(macroc_ctx *c, int op)
 {
     if (!c || (op != MACROC_OP_ASSEMBLED && op != MACROC_OP_MATRIX_FREE && op != MACROC_OP_ASSEMBLED_SYM)) return MACROC_ERR_ARG;
-    if (op == MACROC_OP_ASSEMBLED_SYM) { int rc = sym_supported(c); if (rc) return rc; }
     if (op == MACROC_OP_MATRIX_FREE && c->cfg.material != MACROC_MAT_UNIFORM)
         FAIL(c, MACROC_ERR_UNSUPPORTED, "matrix-free operator needs the uniform tangent");
     c->cfg.op = op;
@@ -1348,7 +1389,7 @@ extern "C" int macroc_get_matrix_blocks(macroc_ctx *c, double *host)
     const int64_t nown = (int64_t)c->g.xm * c->g.ym * c->g.nzl;
     for (int64_t n0 = 0; n0 < nown; n0 += chunk) {
         int64_t nn = std::min<int64_t>(chunk, nown - n0);
-        if (sym) LAUNCH(c, k_export_blocks_sym, cdiv64(nn * 243, 256), 256, c->g, reinterpret_cast<const double *>(c->Asym), n0, nn, tmp, -c->Asym_front * TILE_NODES);
+        if (sym) LAUNCH(c, k_export_blocks_sym, cdiv64(nn * 243, 256), 256, c->g, c->sg, reinterpret_cast<const double *>(c->Asym), n0, nn, tmp);
         else LAUNCH(c, k_export_blocks, cdiv64(nn * 243, 256), 256, c->g, reinterpret_cast<const double *>(c->A), n0, nn, tmp);
         cudaError_t e = cudaMemcpyAsync(host + n0 * 243, tmp, sizeof(double) * 243 * nn, cudaMemcpyDeviceToHost, c->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
@@ -1549,6 +1590,15 @@ extern "C" int macroc_profile_enable(macroc_ctx *c, int enable, int stride)
     c->prof_on = enable != 0;
     c->prof_stride = stride > 0 ? stride : 1;
     c->prof_used = 0; c->prof_counter = 0; c->prof_samples = 0; c->prof_ms = 0.;
+    c->prof_solve_ms = 0.; c->prof_solve_its = 0;
+    return MACROC_OK;
+}
+
+extern "C" int macroc_profile_get_solve(macroc_ctx *c, double *solve_ms_total, int64_t *iterations)
+{
+    if (!c) return MACROC_ERR_ARG;
+    if (solve_ms_total) *solve_ms_total = c->prof_solve_ms;
+    if (iterations) *iterations = c->prof_solve_its;
     return MACROC_OK;
 }
 
@@ -1566,6 +1616,27 @@ extern "C" int macroc_device_synchronize(macroc_ctx *c)
     CU(c, cudaSetDevice(c->device));
     CU(c, cudaStreamSynchronize(c->stream));
     CU(c, cudaStreamSynchronize(c->comm_stream));
+    return MACROC_OK;
+}
+
+extern "C" int macroc_fp64_probe(macroc_ctx *c, double *tflops)
+{
+    if (!c || !tflops) return MACROC_ERR_ARG;
+    CU(c, cudaSetDevice(c->device));
+    const int blocks = 148 * 8;                      // 8 CTAs of 256 threads per SM: every scheduler has 16 warps to pick from
+    double best = 0.;
+    for (int r = 0; r < 6; ++r) {
+        CU(c, cudaEventRecord(c->ev_t0, c->stream));
+        LAUNCH(c, k_fp64_probe, blocks, 256, c->sums, 1.0 + r);
+        CU(c, cudaEventRecord(c->ev_t1, c->stream));
+        CU(c, cudaEventSynchronize(c->ev_t1));
+        float ms = 0.f;
+        CU(c, cudaEventElapsedTime(&ms, c->ev_t0, c->ev_t1));
+        const double flops = 2.0 * FP64_PROBE_CHAINS * (double)FP64_PROBE_ITERS * 256.0 * blocks;
+        if (r >= 1 && ms > 0.f) best = std::max(best, flops / (ms * 1e-3) / 1e12);   // first launch: warm-up
+    }
+    CU(c, cudaGetLastError());
+    *tflops = best;
     return MACROC_OK;
 }
 

@@ -921,4 +921,24 @@ __global__ void k_reduce2(const double *__restrict__ partial, int nblk, double *
     if (threadIdx.x == 0) { out[0] = s0; out[1] = s1; }
 }
 
+// FP64 pipe probe: NCHAIN independent DFMA chains per thread, register operands only.  Used to
+// MEASURE the DFMA rate the FP64-bound kernels (matrix-free apply, element assembly) are compared with.
+constexpr int FP64_PROBE_CHAINS = 16, FP64_PROBE_ITERS = 4096;
+__global__ void __launch_bounds__(256)
+k_fp64_probe(double *out, double seed)
+{
+    double acc[FP64_PROBE_CHAINS];
+    const double m = 1.0 + seed * 1e-9, b = 1e-9 * (threadIdx.x + 1);
+#pragma unroll
+    for (int q = 0; q < FP64_PROBE_CHAINS; ++q) acc[q] = seed + q;
+    for (int it = 0; it < FP64_PROBE_ITERS; ++it) {
+#pragma unroll
+        for (int q = 0; q < FP64_PROBE_CHAINS; ++q) acc[q] = fma(acc[q], m, b);
+    }
+    double s = 0.;
+#pragma unroll
+    for (int q = 0; q < FP64_PROBE_CHAINS; ++q) s += acc[q];
+    if (s == 12345.678) out[0] = s;            // never true: keeps the chains alive
+}
+
 }  // namespace macroc

@@ -41,6 +41,7 @@ constexpr int SYM_PAIRS = 63;
 constexpr int SYM_TILE_DOUBLES = SYM_PAIRS * 2 * TILE_NODES;      // 4032 doubles = 32 256 B
 constexpr int SYM_TILE_BYTES = SYM_TILE_DOUBLES * 8;
 constexpr int SYM_CHUNKS = 7;                          // 7 x 9 pairs = 63
+constexpr int SYM_PRE_CH0 = 2;                         // first chunk that holds a dz = +1 slot (chunk 2: slots 17, 18)
 
 struct SymGeom {
     int rt;                 // x tiles per grid row
@@ -127,13 +128,45 @@ __global__ void k_export_blocks_sym(GridDev g, SymGeom sg, const double *__restr
     out[e] = v;
 }
 
+// x-edge staging: per edge lane 5 neighbour blocks of 5 double2 (the 9 entries + 1) and 5 x 3 vector entries
+constexpr int SYM_EDGE_SLOTS = 5;
+constexpr int SYM_EDGE_DOUBLES = SYM_EDGE_SLOTS * (10 + 3) + 1;             // +1: 16-byte alignment of the next lane's area
+
+__device__ __forceinline__ void cp_async16(void *dst_smem, const void *src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void *dst_smem, const void *src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// L2 eviction-priority policies: 0 evict_first, 1 normal, 2 evict_last
+__device__ __forceinline__ uint64_t l2_policy(int kind)
+{
+    uint64_t pol;
+    if (kind == 0) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    else if (kind == 2) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ double ldg_f64_hint(const double *ptr, uint64_t pol)
+{
+    double v;
+    asm("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(ptr), "l"(pol));
+    return v;
+}
+
 template <int WARPS, int NSTAGE, int RMAX>
 struct SpmvSymSmem {
     static constexpr int ring_bytes = WARPS * NSTAGE * CHUNK_BYTES;
     static constexpr int acc_bytes = WARPS * RMAX * 3 * TILE_NODES * 8;
+    static constexpr int edge_bytes = WARPS * 2 * SYM_EDGE_DOUBLES * 8;      // x-edge staging of lanes 0 and 31
     static constexpr int bar_bytes = WARPS * NSTAGE * 8;
     static constexpr int red_bytes = WARPS * 8;
-    static constexpr int total = ring_bytes + acc_bytes + bar_bytes + red_bytes;
+    static constexpr int total = ring_bytes + acc_bytes + edge_bytes + bar_bytes + red_bytes;
 };
 
 __device__ __forceinline__ double shfl_from_left(double v, int lane)      // value of lane-1, 0 for lane 0
@@ -152,7 +185,8 @@ __device__ __forceinline__ double shfl_from_right(double v, int lane)     // val
 template <int WARPS, int NSTAGE, int RMAX, bool DOT>
 __global__ void __launch_bounds__(WARPS * 32, 1)
 k_spmv_sym(GridDev g, SymGeom sg, const double2 *__restrict__ A, const double *__restrict__ p, double *__restrict__ w,
-           int zA, int zB, int R, int nseg, double *__restrict__ partial, const int *__restrict__ done)
+           int zA, int zB, int R, int nseg, double *__restrict__ partial, const int *__restrict__ done,
+           int hint /* L2 policies, 2 bits each: [1:0] operator stream (0 evict_first), [3:2] vector loads (0 default) */)
 {
     using SM = SpmvSymSmem<WARPS, NSTAGE, RMAX>;
     extern __shared__ __align__(128) unsigned char smem_ring[];
@@ -160,8 +194,11 @@ k_spmv_sym(GridDev g, SymGeom sg, const double2 *__restrict__ A, const double *_
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned char *ring = smem_ring + (size_t)warp * NSTAGE * CHUNK_BYTES;
     double *acc = reinterpret_cast<double *>(smem_ring + SM::ring_bytes) + (size_t)warp * RMAX * 3 * TILE_NODES + lane;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_ring + SM::ring_bytes + SM::acc_bytes) + warp * NSTAGE;
-    double *red = reinterpret_cast<double *>(smem_ring + SM::ring_bytes + SM::acc_bytes + SM::bar_bytes);
+    // lanes 0 and 31 stage the blocks of their x neighbours (other x tile) one tile step ahead
+    double *edge = reinterpret_cast<double *>(smem_ring + SM::ring_bytes + SM::acc_bytes) +
+                   ((size_t)warp * 2 + (lane == 31 ? 1 : 0)) * SYM_EDGE_DOUBLES;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_ring + SM::ring_bytes + SM::acc_bytes + SM::edge_bytes) + warp * NSTAGE;
+    double *red = reinterpret_cast<double *>(smem_ring + SM::ring_bytes + SM::acc_bytes + SM::edge_bytes + SM::bar_bytes);
     if (lane == 0) {
 #pragma unroll
         for (int s = 0; s < NSTAGE; ++s) mbar_init(&bars[s], 1);
@@ -169,7 +206,8 @@ k_spmv_sym(GridDev g, SymGeom sg, const double2 *__restrict__ A, const double *_
     }
     __syncwarp();
     const unsigned char *Ab = reinterpret_cast<const unsigned char *>(A);
-    const uint64_t policy = l2_evict_first_policy();
+    const uint64_t policy = l2_policy(hint & 3);
+    const uint64_t ppol = l2_policy(((hint >> 2) & 3) == 0 ? 1 : ((hint >> 2) & 3) == 1 ? 2 : 0);
     const int64_t NX = g.NX, npl = g.npl;
     const int ybands = (g.NY + R - 1) / R;
     const int64_t items = (int64_t)sg.rt * ybands * nseg;
@@ -184,25 +222,105 @@ k_spmv_sym(GridDev g, SymGeom sg, const double2 *__restrict__ A, const double *_
         if (z0 >= z1) continue;                                      // warp-uniform
         const bool pre = z0 - 1 >= sg.zmin;                          // scatter-only pass over the plane below the segment
         const int zfirst = pre ? z0 - 1 : z0;
-        const int64_t ntile = (int64_t)(z1 - zfirst) * rows, nch = ntile * SYM_CHUNKS;
+        // the scatter-only pass needs the dz = +1 slots only: chunks SYM_PRE_CH0..6 (slots 17..26)
+        const int64_t nch = (int64_t)(z1 - z0) * rows * SYM_CHUNKS + (pre ? (int64_t)rows * (SYM_CHUNKS - SYM_PRE_CH0) : 0);
         const int64_t c0 = c;
-        // chunk qi of this item's sequence: tile (xt, y0 + r, zfirst + zi), r fastest
-        auto issue = [&](int64_t qi) {
-            const int64_t ts = qi / SYM_CHUNKS;
-            const int ch = (int)(qi - ts * SYM_CHUNKS);
-            const int zi = (int)(ts / rows), r = (int)(ts - (int64_t)zi * rows);
-            const int64_t tq = sym_tile_index(g, sg, xt, y0 + r, zfirst + zi);
-            const int stage = (int)((c0 + qi) % NSTAGE);
+        // the item's chunk sequence: tiles (xt, y0 + r, z), r fastest, 7 chunks each.  Lane 0 walks it
+        // with counters (no divisions on the critical path); iq = chunks issued so far
+        int64_t iq = 0;
+        int i_ch = pre ? SYM_PRE_CH0 : 0, i_r = 0, i_z = zfirst;
+        auto issue_next = [&]() {
+            const int64_t tq = sym_tile_index(g, sg, xt, y0 + i_r, i_z);
+            const int stage = (int)((c0 + iq) % NSTAGE);
             mbar_arrive_expect_tx(&bars[stage], CHUNK_BYTES);
-            tma_load_bulk(ring + stage * CHUNK_BYTES, Ab + tq * (int64_t)SYM_TILE_BYTES + (int64_t)ch * CHUNK_BYTES,
+            tma_load_bulk(ring + stage * CHUNK_BYTES, Ab + tq * (int64_t)SYM_TILE_BYTES + (int64_t)i_ch * CHUNK_BYTES,
                           (uint32_t)CHUNK_BYTES, &bars[stage], policy);
+            ++iq;
+            if (++i_ch == SYM_CHUNKS) {
+                if (++i_r == rows) { i_r = 0; ++i_z; }
+                i_ch = i_z < z0 ? SYM_PRE_CH0 : 0;
+            }
         };
         if (lane == 0)
-            for (int64_t qi = 0; qi < NSTAGE && qi < nch; ++qi) issue(qi);
+            for (int qi = 0; qi < NSTAGE && qi < nch; ++qi) issue_next();
         // the accumulator plane starts empty (also orders it after the previous item's last reads)
         for (int r = 0; r < rows; ++r) { acc[(r * 3 + 0) * TILE_NODES] = 0.; acc[(r * 3 + 1) * TILE_NODES] = 0.; acc[(r * 3 + 2) * TILE_NODES] = 0.; }
         const int x = xt * 32 + lane;
         const bool xvalid = x < g.NX;
+        // lanes whose x neighbour lives in another x tile: lane 0 looks left (slots with ddx = +1),
+        // lane 31 looks right (ddx = -1)
+        const bool edge_lane = (lane == 0 && x > 0) || (lane == 31 && x + 1 < g.NX);
+        const int exj = lane == 0 ? x - 1 : x + 1;
+        auto edge_slot = [&](int e, int yy, int zz, int &sl, int &yj, int &zj) -> bool {
+            // lane 0: slots 14 17 20 23 26; lane 31: slots 15 18 21 24
+            sl = lane == 0 ? 14 + 3 * e : 15 + 3 * e;
+            if (sl > 26) return false;
+            yj = yy - ((sl / 3) % 3 - 1); zj = zz - (sl / 9 - 1);
+            return yj >= 0 && yj < g.NY && zj >= sg.zmin;
+        };
+        auto edge_stage = [&](int yy, int zz) {
+#pragma unroll
+            for (int e = 0; e < SYM_EDGE_SLOTS; ++e) {
+                int sl, yj, zj;
+                if (edge_slot(e, yy, zz, sl, yj, zj)) {
+                    const double2 *bj = A + sym_tile_index(g, sg, exj >> 5, yj, zj) * (SYM_PAIRS * TILE_NODES) + (exj & 31);
+                    const int k0s = (sl - 13) * 9;
+#pragma unroll
+                    for (int qq = 0; qq < 5; ++qq) cp_async16(edge + e * 10 + 2 * qq, bj + ((k0s >> 1) + qq) * TILE_NODES);
+                    const double *pj = p + g.G + exj + NX * yj + npl * zj;
+#pragma unroll
+                    for (int d = 0; d < 3; ++d) cp_async8(edge + 10 * SYM_EDGE_SLOTS + 3 * e + d, pj + d * g.S);
+                }
+            }
+            cp_async_commit();
+        };
+        auto edge_apply = [&](int yy, int zz, double &a0, double &a1, double &a2) {
+#pragma unroll
+            for (int e = 0; e < SYM_EDGE_SLOTS; ++e) {
+                int sl, yj, zj;
+                if (edge_slot(e, yy, zz, sl, yj, zj)) {
+                    const double *m = edge + e * 10 + (((sl - 13) * 9) & 1);
+                    const double x0 = edge[10 * SYM_EDGE_SLOTS + 3 * e], x1 = edge[10 * SYM_EDGE_SLOTS + 3 * e + 1],
+                                 x2 = edge[10 * SYM_EDGE_SLOTS + 3 * e + 2];
+                    // w_i[c] += sum_r A[j][s][r][c] * p_j[r]
+                    a0 = fma(m[0], x0, a0); a0 = fma(m[3], x1, a0); a0 = fma(m[6], x2, a0);
+                    a1 = fma(m[1], x0, a1); a1 = fma(m[4], x1, a1); a1 = fma(m[7], x2, a1);
+                    a2 = fma(m[2], x0, a2); a2 = fma(m[5], x1, a2); a2 = fma(m[8], x2, a2);
+                }
+            }
+        };
+        // slots sA, sA+1, sA+2 (ddx = -1, 0, +1; common ddy, ddz) of the row above / below the band,
+        // sources inside this x tile only (the other lanes are served by the x-edge staging)
+        auto gather3 = [&](int sA, int yy, int zz, double &a0, double &a1, double &a2) {
+            const int ddy = (sA / 3) % 3 - 1, ddz = sA / 9 - 1;
+            const int yj = yy - ddy, zj = zz - ddz;
+            if (yj < 0 || yj >= g.NY || zj < sg.zmin) return;       // warp-uniform
+            const double2 *bt = A + sym_tile_index(g, sg, xt, yj, zj) * (SYM_PAIRS * TILE_NODES);
+            const double *pt = p + g.G + (int64_t)xt * 32 + NX * yj + npl * zj;
+            double2 pr[3][5];
+            double xx[3][3];
+            bool ok[3];
+#pragma unroll
+            for (int u = 0; u < 3; ++u) {
+                const int sl = lane - (u - 1);                       // source lane
+                ok[u] = xvalid && sl >= 0 && sl <= 31;
+                const int slc = ok[u] ? sl : lane;
+                const int k0s = (sA + u - 13) * 9;
+#pragma unroll
+                for (int e = 0; e < 5; ++e) pr[u][e] = __ldg(bt + ((k0s >> 1) + e) * TILE_NODES + slc);
+#pragma unroll
+                for (int d = 0; d < 3; ++d) xx[u][d] = ok[u] ? __ldg(pt + d * g.S + slc) : 0.;
+            }
+#pragma unroll
+            for (int u = 0; u < 3; ++u) {
+                const double *m = reinterpret_cast<const double *>(pr[u]) + (((sA + u - 13) * 9) & 1);
+                a0 = fma(m[0], xx[u][0], a0); a0 = fma(m[3], xx[u][1], a0); a0 = fma(m[6], xx[u][2], a0);
+                a1 = fma(m[1], xx[u][0], a1); a1 = fma(m[4], xx[u][1], a1); a1 = fma(m[7], xx[u][2], a1);
+                a2 = fma(m[2], xx[u][0], a2); a2 = fma(m[5], xx[u][1], a2); a2 = fma(m[8], xx[u][2], a2);
+            }
+        };
+        // the first step of the item gathers already (no scatter-only pass below): stage it now
+        if (!pre && edge_lane) edge_stage(y0, z0);
         int64_t q = 0;
         for (int z = zfirst; z < z1; ++z) {
             const bool scatter_only = z < z0;
@@ -214,51 +332,53 @@ k_spmv_sym(GridDev g, SymGeom sg, const double2 *__restrict__ A, const double *_
                 const int y = y0 + r;
                 const int64_t ln = x + NX * y + npl * z;
                 const double *p0 = p + g.G + ln, *p1 = p0 + g.S, *p2 = p1 + g.S;
-                const double pc0 = __ldg(p0), pc1 = __ldg(p1), pc2 = __ldg(p2);
+                const double pc0 = ldg_f64_hint(p0, ppol), pc1 = ldg_f64_hint(p1, ppol), pc2 = ldg_f64_hint(p2, ppol);
                 // what the plane below and the previous row of this plane scattered to this node
                 double a0 = acc[(r * 3 + 0) * TILE_NODES] + carry0, a1 = acc[(r * 3 + 1) * TILE_NODES] + carry1,
                        a2 = acc[(r * 3 + 2) * TILE_NODES] + carry2;
-                // (1) blocks of neighbours outside the band (x tile edge, first / last row): ordinary loads
+                // (1a) x tile edge (lanes 0 / 31): the neighbour's blocks were staged one tile step ahead
+                if (!scatter_only && edge_lane) {
+                    cp_async_wait_all();
+                    edge_apply(y, z, a0, a1, a2);
+                }
+                {
+                    // stage the next step's (r+1 of this plane, or row 0 of the next plane)
+                    const bool last_row = r + 1 == rows;
+                    const int zn = last_row ? z + 1 : z, yn = last_row ? y0 : y + 1;
+                    if (edge_lane && zn < z1 && zn >= z0) edge_stage(yn, zn);
+                }
+                // (1b) first / last row of the band: the rows above / below belong to another band.  Three
+                // slots (ddx = -1, 0, +1) per group, all loads of a group in flight together
                 if (!scatter_only) {
-#pragma unroll
-                    for (int s = 14; s < 27; ++s) {
-                        const int ddx = s % 3 - 1, ddy = (s / 3) % 3 - 1, ddz = s / 9 - 1;
-                        const int xj = x - ddx, yj = y - ddy, zj = z - ddz;
-                        const bool outside = (lane - ddx < 0) || (lane - ddx > 31) || (r - ddy < 0) || (r - ddy >= rows);
-                        const bool need = xvalid && outside && xj >= 0 && xj < g.NX && yj >= 0 && yj < g.NY && zj >= sg.zmin;
-                        if (__any_sync(0xffffffffu, need)) {
-                            if (need) {
-                                const int64_t off = ddx + NX * ddy + npl * ddz;
-                                const double x0 = __ldg(p0 - off), x1 = __ldg(p1 - off), x2 = __ldg(p2 - off);
-                                const double2 *bj = A + sym_tile_index(g, sg, xj >> 5, yj, zj) * (SYM_PAIRS * TILE_NODES) + (xj & 31);
-                                const int k0s = (s - 13) * 9;
-                                double2 pr[5];
-#pragma unroll
-                                for (int e = 0; e < 5; ++e) pr[e] = __ldg(bj + ((k0s >> 1) + e) * TILE_NODES);
-                                const double *m = reinterpret_cast<const double *>(pr) + (k0s & 1);
-                                // w_i[c] += sum_r A[j][s][r][c] * p_j[r]
-                                a0 = fma(m[0], x0, a0); a0 = fma(m[3], x1, a0); a0 = fma(m[6], x2, a0);
-                                a1 = fma(m[1], x0, a1); a1 = fma(m[4], x1, a1); a1 = fma(m[7], x2, a1);
-                                a2 = fma(m[2], x0, a2); a2 = fma(m[5], x1, a2); a2 = fma(m[8], x2, a2);
-                            }
-                        }
-                    }
+                    if (r == 0) { gather3(15, y, z, a0, a1, a2); gather3(24, y, z, a0, a1, a2); }
+                    if (r == rows - 1) gather3(18, y, z, a0, a1, a2);
                 }
                 // (2) own blocks (slots 13..26) from the TMA ring: row i, and the transposed use for row i + off
                 double nc0 = 0., nc1 = 0., nc2 = 0.;                 // carry for the next row
-#pragma unroll
-                for (int ch = 0; ch < SYM_CHUNKS; ++ch, ++q, ++c) {
-                    const int stage = (int)(c % NSTAGE);
-                    const uint32_t parity = (uint32_t)((c / NSTAGE) & 1);
-                    double xv[2][3];
+                // vector operands of a chunk's two slots, fetched one chunk ahead of their use (the
+                // mbarrier wait is a scheduling fence: loads issued after it would expose their latency)
+                auto load_xv = [&](int ch, double (&xq)[2][3]) {
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
                         const int slot = 13 + 2 * ch + h;
                         const int ddx = slot % 3 - 1, ddy = (slot / 3) % 3 - 1, ddz = slot / 9 - 1;
                         const int64_t off = ddx + NX * ddy + npl * ddz;
-                        if (slot == 13) { xv[h][0] = pc0; xv[h][1] = pc1; xv[h][2] = pc2; }
-                        else { xv[h][0] = __ldg(p0 + off); xv[h][1] = __ldg(p1 + off); xv[h][2] = __ldg(p2 + off); }
+                        if (slot == 13) { xq[h][0] = pc0; xq[h][1] = pc1; xq[h][2] = pc2; }
+                        else { xq[h][0] = ldg_f64_hint(p0 + off, ppol); xq[h][1] = ldg_f64_hint(p1 + off, ppol); xq[h][2] = ldg_f64_hint(p2 + off, ppol); }
                     }
+                };
+                double xnext[2][3];
+                if (scatter_only) load_xv(SYM_PRE_CH0, xnext); else load_xv(0, xnext);
+#pragma unroll
+                for (int ch = 0; ch < SYM_CHUNKS; ++ch) {
+                    if (scatter_only && ch < SYM_PRE_CH0) continue;      // warp-uniform: these chunks were not streamed
+                    const int stage = (int)(c % NSTAGE);
+                    const uint32_t parity = (uint32_t)((c / NSTAGE) & 1);
+                    ++q; ++c;
+                    double xv[2][3];
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) { xv[h][0] = xnext[h][0]; xv[h][1] = xnext[h][1]; xv[h][2] = xnext[h][2]; }
+                    if (ch + 1 < SYM_CHUNKS) load_xv(ch + 1, xnext);
                     mbar_wait(&bars[stage], parity);
                     const double2 *sv = reinterpret_cast<const double2 *>(ring + stage * CHUNK_BYTES) + lane;
                     double2 v[9];
@@ -287,7 +407,7 @@ k_spmv_sym(GridDev g, SymGeom sg, const double2 *__restrict__ A, const double *_
                         }
                     }
                     __syncwarp();
-                    if (lane == 0 && q + NSTAGE < nch) issue(q + NSTAGE);
+                    if (lane == 0 && iq < nch) issue_next();
                 }
                 carry0 = nc0; carry1 = nc1; carry2 = nc2;
                 if (!scatter_only && xvalid) {

@@ -2,7 +2,7 @@
  * dropin_glue.c -- the reference-side binding of include/macroc_b200.h.
  *
  * Compiled TOGETHER WITH the reference's own, unmodified src/main.c, init.c, forces.c, output.c
- * and util.c (oracle/Makefile, target `dropin`): this file takes the place of src/assembly.c and
+ * and util.c (the `dropin` build recipe): this file takes the place of src/assembly.c and
  * src/bcs.c and forwards every function they define (include/macroc.h:130-155) to the C ABI.
  * main.c's Newton loop (src/main.c:53-82), init.c's option parsing and printing, forces.c's
  * reaction force and output.c's VTU writer run as they are; MicroPP (here: its linear-elastic

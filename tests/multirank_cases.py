@@ -39,7 +39,7 @@ def cases_for(world, which="all"):
 
 
 VARIANTS = [(M.OP_ASSEMBLED, M.MAT_UNIFORM), (M.OP_MATRIX_FREE, M.MAT_UNIFORM), (M.OP_ASSEMBLED, M.MAT_PER_GP),
-            (M.OP_ASSEMBLED_SYM, M.MAT_UNIFORM)]
+            (M.OP_ASSEMBLED_SYM, M.MAT_UNIFORM), (M.OP_ASSEMBLED_SYM, M.MAT_PER_GP)]
 
 
 def run_cases(comm, device, make_id, cases, variants=VARIANTS, log=None):
@@ -86,7 +86,11 @@ def run_cases(comm, device, make_id, cases, variants=VARIANTS, log=None):
                 for g in got:
                     u.reshape(-1, 3)[g[5]] = g[0].reshape(-1, 3); y.reshape(-1, 3)[g[5]] = g[1].reshape(-1, 3)
                 eu = rel_err(u, o.get_vec("u"))
-                assert eu < 1e-9, (NX, NY, NZ, bc, pg, op, material, eu)
+                if not eu < 1e-9:                            # say which rank, and how its history went
+                    uo = o.get_vec("u").reshape(-1, 3)
+                    per_rank = [float(np.abs(g[0].reshape(-1, 3) - uo[g[5]]).max() / np.abs(uo).max()) for g in got]
+                    raise AssertionError((NX, NY, NZ, bc, pg, op, material, eu, per_rank, [g[3] for g in got][:2],
+                                          [(l.newton_its, l.ksp_its) for l in ologs]))
                 o.assembly_jac()
                 ey_ = rel_err(y, o.matmult(x))
                 assert ey_ < 1e-13, (NX, NY, NZ, bc, pg, op, material, ey_)

@@ -21,7 +21,7 @@ def run_bench(args, timeout):
 
 
 def test_reference_arm_line():
-    d = run_bench(["--impl", "reference", "--steps", "1", "--warmup", "0", "--cg-its", "100"], 600)
+    d = run_bench(["--impl", "reference", "--steps", "1", "--warmup", "1", "--cg-its", "100", "--cpu-grid", "40"], 600)
     assert BASE_KEYS <= set(d)
     assert d["impl"] == "reference" and d["metric"] == "newton_step_dof_per_s" and d["unit"] == "DOF/s"
     assert d["higher_is_better"] is True and d["dtype"] == "f64" and d["vs_baseline"] is None
@@ -29,6 +29,23 @@ def test_reference_arm_line():
     assert d["cpu_baseline"]["value"] == d["value"] == d["e2e"]["value"]
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert "workload" in d["config"] and "model" not in d["config"]
+    ms = d["cpu_baseline"]["measured_step"]                 # a genuinely timed full Newton step, not a model
+    assert ms["measured_grid"] == [40, 40, 40] and ms["measured_cg_iterations"] > 10 and ms["measured_step_s"] > 0
+    assert 0.3 < d["cpu_baseline"]["model_over_measured"] < 3.0
+
+
+def test_both_arms_describe_the_same_config():
+    """`config` must be the same object in both arms (the driver compares them)."""
+    sys.path.insert(0, ROOT)
+    import bench
+    a = bench.bench_config(256, 256, 256, 1, "assembled", False)
+    assert a == bench.bench_config(256, 256, 256, 1, "assembled", False)
+    assert set(a) == {"workload", "grid", "ndof", "operator", "parallelism", "ksp", "l2"}
+
+
+def test_bench_does_not_write_into_the_repo():
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    assert "json.dump(" not in src and "open(KNOWN" not in src
 
 
 @pytest.mark.gpu
@@ -42,6 +59,9 @@ def test_gpu_arm_line_small_grid():
     r = d["roofline"]
     assert r["bound"] == "hbm" and r["unit"] == "GB/s" and r["achieved"] > 0 and r["peak"] > 0
     assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
-    assert d["config"]["newton_its_per_step"] == [1, 1]
-    assert d["matrix_free"]["cg_iterations"] == pytest.approx(d["config"]["cg_iterations_per_step"], abs=2)
-    assert "assembled_sym" in d              # its numbers are checked in test_gpu_parity.py (symmetric storage)
+    assert d["newton_its_per_step"] == [1, 1]
+    assert d["matrix_free"]["cg_iterations"] == pytest.approx(d["cg_iterations_per_step"], abs=2)
+    other = d["assembled_sym"] if d["config"]["operator"] == "assembled" else d["assembled_full"]
+    assert other["cg_iterations"] == pytest.approx(d["cg_iterations_per_step"], abs=2)
+    assert d["cg_iteration_ms"] > 0 and d["fp64"]["dfma_tflops_measured"] > 1.0
+    assert "jacobian_per_element_per_gp" in d["kernels_ms"]

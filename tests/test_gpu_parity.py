@@ -234,9 +234,11 @@ def test_c_host_driver_log_matches_reference(name, tmp_path):
 
 @pytest.mark.parametrize("NX,NY,NZ,bc,extra", [GRIDS[0], GRIDS[2], GRIDS[6], GRIDS[7], GRIDS[8], GRIDS[10]])
 @pytest.mark.parametrize("material,jac_mode", [(M.MAT_UNIFORM, M.JAC_ELEMENT), (M.MAT_PER_GP, M.JAC_AUTO)])
-def test_element_kernels_match_oracle(NX, NY, NZ, bc, extra, material, jac_mode):
+@pytest.mark.parametrize("op", [M.OP_ASSEMBLED, M.OP_ASSEMBLED_SYM])
+def test_element_kernels_match_oracle(NX, NY, NZ, bc, extra, material, jac_mode, op):
+    """k_assemble_elements into the full 27-slot layout and into the symmetric 14-slot row tiles."""
     o = O.Oracle(O.Config(NX=NX, NY=NY, NZ=NZ, bc_type=bc, faithful_ke=0, **extra))
-    m = M.MacroC(M.Config(NX=NX, NY=NY, NZ=NZ, bc_type=bc, material=material, jac_mode=jac_mode, **extra))
+    m = M.MacroC(M.Config(NX=NX, NY=NY, NZ=NZ, bc_type=bc, material=material, jac_mode=jac_mode, op=op, **extra))
     u0 = 1e-3 * np.random.default_rng(11).standard_normal(o.ndof)
     o.set_vec("u", u0); m.set_vec(M.VEC_U, u0)
     U = o.get_displacement(2)
@@ -253,21 +255,22 @@ def test_element_kernels_match_oracle(NX, NY, NZ, bc, extra, material, jac_mode)
     # and the whole loop
     o2 = O.Oracle(O.Config(NX=NX, NY=NY, NZ=NZ, bc_type=bc, ts=3, rtol=1e-12, faithful_ke=0, **extra))
     m2 = M.MacroC(M.Config(NX=NX, NY=NY, NZ=NZ, bc_type=bc, ts=3, ksp_rtol=1e-12, material=material,
-                           jac_mode=jac_mode, **extra))
+                           jac_mode=jac_mode, op=op, **extra))
     logs = o2.run()
     for t in range(3):
         assert m2.time_step(t)["newton_its"] == logs[t].newton_its
     assert rel_err(m2.get_vec(M.VEC_U), o2.get_vec("u")) < TOL_U
 
 
-def test_heterogeneous_gauss_point_data():
+@pytest.mark.parametrize("op", [M.OP_ASSEMBLED, M.OP_ASSEMBLED_SYM])
+@pytest.mark.parametrize("NX,NY,NZ", [(7, 4, 5), (37, 5, 4)])
+def test_heterogeneous_gauss_point_data(op, NX, NY, NZ):
     """Every Gauss point gets its own SPD tangent and stress (what a GPU material model would
     write): the assembled operator and residual must equal an element-by-element assembly with
     the oracle's element routines (reference loops assembly.c:94-99, :151-153)."""
     import scipy.sparse as sp
-    NX, NY, NZ = 7, 4, 5
     rng = np.random.default_rng(5)
-    m = M.MacroC(M.Config(NX=NX, NY=NY, NZ=NZ, bc_type=M.BC_BENDING, material=M.MAT_PER_GP))
+    m = M.MacroC(M.Config(NX=NX, NY=NY, NZ=NZ, bc_type=M.BC_BENDING, material=M.MAT_PER_GP, op=op))
     o = O.Oracle(O.Config(NX=NX, NY=NY, NZ=NZ, bc_type=M.BC_BENDING))
     ne = (NX - 1) * (NY - 1) * (NZ - 1)
     Q = rng.standard_normal((ne, 8, 6, 6))
@@ -295,7 +298,7 @@ def test_heterogeneous_gauss_point_data():
     A_ref = csr_to_block_stencil(A.indptr, A.indices, A.data, NX, NY, NZ)
     assert rel_err(m.get_matrix_blocks(), A_ref) < TOL_MAT
     x = rng.standard_normal(n)
-    assert rel_err(m.matmult(x), A @ x) < 1e-13
+    assert rel_err(m.matmult(x, op), A @ x) < 1e-13
 
 
 def test_two_live_contexts_do_not_share_element_constants():
