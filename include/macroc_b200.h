@@ -84,7 +84,12 @@ typedef struct {
     int32_t physical_B;            /* 0 (default): the reference's calc_B, whose local dx=dy=dz=1
                                       makes B that of a unit cube (assembly.c:198); 1: B of the
                                       physical element (-physical_B 1)                       */
-    int32_t reserved[5];
+    int32_t strict_fp;             /* 0 (default): production kernels (FMA, tree reductions).
+                                      1: verification mode -- the reference's rounding: no FMA contraction,
+                                      CSR-order row sums, sequential dots (csrc/strict_fp.cuh).  One rank,
+                                      uniform tangent, MACROC_OP_ASSEMBLED; reproduces the reference binary
+                                      bit for bit and is orders of magnitude slower (-strict_fp 1)          */
+    int32_t reserved[4];
 } macroc_config;
 
 typedef struct macroc_ctx macroc_ctx;

@@ -62,7 +62,8 @@ class CConfig(C.Structure):
         ("D", C.c_double * 36),
         ("use_D", C.c_int32), ("op", C.c_int32), ("device", C.c_int32),
         ("material", C.c_int32), ("jac_mode", C.c_int32), ("physical_B", C.c_int32),
-        ("reserved", C.c_int32 * 5),
+        ("strict_fp", C.c_int32),
+        ("reserved", C.c_int32 * 4),
     ]
 
 
@@ -173,6 +174,7 @@ class Config:
     material: int = MAT_UNIFORM
     jac_mode: int = JAC_AUTO
     physical_B: int = 0
+    strict_fp: int = 0
     D: np.ndarray | None = None
 
     def to_c(self) -> CConfig:
@@ -180,7 +182,7 @@ class Config:
         lib().macroc_default_config(C.byref(c))
         for k in ("NX", "NY", "NZ", "px", "py", "pz", "lx", "ly", "lz", "bc_type", "ts", "dt", "final_time",
                   "newton_max_its", "newton_min_tol", "newton_rel_tol", "ksp_rtol", "ksp_abstol", "ksp_dtol",
-                  "ksp_maxits", "E", "nu", "op", "device", "material", "jac_mode", "physical_B"):
+                  "ksp_maxits", "E", "nu", "op", "device", "material", "jac_mode", "physical_B", "strict_fp"):
             setattr(c, k, getattr(self, k))
         if self.D is not None:
             d = np.ascontiguousarray(self.D, dtype=np.float64).reshape(36)

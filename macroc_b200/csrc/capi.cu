@@ -27,6 +27,8 @@
 #include "assembly_elem.cuh"
 #include "spmv_sym.cuh"
 #include "loopback.h"
+#include "cg_mbox.cuh"
+#include "strict_fp.cuh"
 
 using namespace macroc;
 
@@ -44,6 +46,12 @@ struct macroc_ctx {
     cudaEvent_t ev_ready = nullptr, ev_halo = nullptr, ev_t0 = nullptr, ev_t1 = nullptr, ev_chk[2] = {nullptr, nullptr};
     ncclComm_t comm = nullptr;
     LoopGroup *loop = nullptr;       // in-process communicator (loopback.h) instead of NCCL
+    // CG all-reduces through peer-mapped mailboxes (cg_mbox.cuh); NCCL all-reduce when the mapping is unavailable
+    double *mbox = nullptr;          // this rank's mailbox: [2 parities][nranks][4 doubles]
+    double **mbox_peers = nullptr;   // device table of every rank's mailbox as mapped here
+    void *mbox_opened[MBOX_MAX_RANKS] = {nullptr};
+    bool mbox_on = false;
+    unsigned long long mbox_seq = 0;
     double *vec[V_COUNT] = {nullptr};
     double2 *A = nullptr;
     double2 *Asym = nullptr;         // symmetric storage (14 of 27 slots), MACROC_OP_ASSEMBLED_SYM; points at tile 0
@@ -240,6 +248,8 @@ extern "C" int macroc_config_from_args(macroc_config *cfg, int argc, const char 
             double a = 0, b = 0;
             if (sscanf(v, "%lf,%lf", &a, &b) == 2) { cfg->E = a; cfg->nu = b; }
         } else if (is("-mat_free")) cfg->op = atoi(v) ? MACROC_OP_MATRIX_FREE : MACROC_OP_ASSEMBLED;
+        else if (is("-strict_fp")) cfg->strict_fp = atoi(v);
+        else if (is("-physical_B")) cfg->physical_B = atoi(v);
         else if (is("-ksp_type")) { if (strcmp(v, "cg") != 0) return MACROC_ERR_UNSUPPORTED; }
         else if (is("-pc_type")) { if (strcmp(v, "jacobi") != 0) return MACROC_ERR_UNSUPPORTED; }
     }
@@ -328,6 +338,8 @@ static int ctx_free(macroc_ctx *c)
     if (!c) return MACROC_OK;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    for (void *ptr : c->mbox_opened) if (ptr) cudaIpcCloseMemHandle(ptr);
+    cudaFree(c->mbox_peers); cudaFree(c->mbox);
     if (c->comm) ncclCommDestroy(c->comm);
     if (c->loop) {
         // the last member to leave frees the group; a member that leaves early breaks it for the rest
@@ -366,6 +378,60 @@ static int ctx_free(macroc_ctx *c)
 
 extern "C" int macroc_destroy(macroc_ctx *ctx) { return ctx_free(ctx); }
 
+// Peer-mapped mailboxes for the CG all-reduces (cg_mbox.cuh): every rank allocates one, the cudaIpc
+// handles travel through an ncclAllGather, each rank maps its peers' mailboxes.  Every step is
+// optional: if any rank cannot map its peers (no IPC in the container, no P2P between the GPUs,
+// MACROC_ALLREDUCE=nccl), ALL ranks fall back to ncclAllReduce -- the decision is itself all-reduced.
+static int mbox_setup(macroc_ctx *c)
+{
+    const int n = c->slab.nranks, me = c->slab.rank;
+    int ok = 1;
+    if (const char *v = getenv("MACROC_ALLREDUCE")) if (strcmp(v, "nccl") == 0) ok = 0;
+    if (n > MBOX_MAX_RANKS) ok = 0;
+    const size_t bytes = sizeof(double) * 2 * (size_t)n * MBOX_SLOT_DOUBLES;
+    cudaIpcMemHandle_t mine;
+    memset(&mine, 0, sizeof(mine));
+    unsigned char *stage = nullptr;                   // [n][64] handles + [n] flags
+    const size_t hs = sizeof(cudaIpcMemHandle_t);
+    CU(c, cudaMalloc(&stage, (size_t)n * hs + sizeof(int) * 2));
+    if (ok && (cudaMalloc(&c->mbox, bytes) != cudaSuccess || cudaMemset(c->mbox, 0, bytes) != cudaSuccess ||
+               cudaIpcGetMemHandle(&mine, c->mbox) != cudaSuccess)) { cudaGetLastError(); ok = 0; }
+    std::vector<unsigned char> all((size_t)n * hs);
+    cudaError_t e = cudaMemcpy(stage + (size_t)me * hs, &mine, hs, cudaMemcpyHostToDevice);
+    ncclResult_t ne = ncclSuccess;
+    if (e == cudaSuccess) ne = ncclAllGather(stage + (size_t)me * hs, stage, hs, ncclUint8, c->comm, c->stream);
+    if (e == cudaSuccess && ne == ncclSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e == cudaSuccess && ne == ncclSuccess) e = cudaMemcpy(all.data(), stage, (size_t)n * hs, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess || ne != ncclSuccess) { cudaFree(stage); FAIL(c, MACROC_ERR_NCCL, "mailbox setup: exchanging the IPC handles failed"); }
+    std::vector<double *> peers((size_t)n, nullptr);
+    if (ok) {
+        for (int q = 0; q < n && ok; ++q) {
+            if (q == me) { peers[(size_t)q] = c->mbox; continue; }
+            cudaIpcMemHandle_t h;
+            memcpy(&h, all.data() + (size_t)q * hs, hs);
+            void *ptr = nullptr;
+            if (cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = 0; break; }
+            c->mbox_opened[q] = ptr;
+            peers[(size_t)q] = (double *)ptr;
+        }
+    }
+    // unanimous?
+    int *flag = reinterpret_cast<int *>(stage + (size_t)n * hs);
+    e = cudaMemcpy(flag, &ok, sizeof(int), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) ne = ncclAllReduce(flag, flag + 1, 1, ncclInt, ncclMin, c->comm, c->stream);
+    if (e == cudaSuccess && ne == ncclSuccess) e = cudaStreamSynchronize(c->stream);
+    int all_ok = 0;
+    if (e == cudaSuccess && ne == ncclSuccess) e = cudaMemcpy(&all_ok, flag + 1, sizeof(int), cudaMemcpyDeviceToHost);
+    cudaFree(stage);
+    if (e != cudaSuccess || ne != ncclSuccess) FAIL(c, MACROC_ERR_NCCL, "mailbox setup: agreeing on the all-reduce path failed");
+    if (all_ok) {
+        CU(c, cudaMalloc(&c->mbox_peers, sizeof(double *) * (size_t)n));
+        CU(c, cudaMemcpy(c->mbox_peers, peers.data(), sizeof(double *) * (size_t)n, cudaMemcpyHostToDevice));
+        c->mbox_on = true;
+    }
+    return MACROC_OK;
+}
+
 extern "C" int macroc_create(const macroc_config *cfg, int rank, int nranks, const void *id128, macroc_ctx **out)
 {
     if (!cfg || !out) FAIL((macroc_ctx *)nullptr, MACROC_ERR_ARG, "macroc_create: null argument");
@@ -384,6 +450,10 @@ extern "C" int macroc_create(const macroc_config *cfg, int rank, int nranks, con
         FAIL((macroc_ctx *)nullptr, MACROC_ERR_ARG, "macroc_create: unknown jac_mode %d", (int)cfg->jac_mode);
     if (cfg->ksp_maxits < 0 || cfg->newton_max_its < 0)
         FAIL((macroc_ctx *)nullptr, MACROC_ERR_ARG, "macroc_create: negative iteration limit");
+    if (cfg->strict_fp && (nranks != 1 || cfg->material != MACROC_MAT_UNIFORM || cfg->op != MACROC_OP_ASSEMBLED ||
+                           cfg->jac_mode != MACROC_JAC_AUTO))
+        FAIL((macroc_ctx *)nullptr, MACROC_ERR_UNSUPPORTED, "macroc_create: strict_fp is a one-rank verification mode "
+             "(uniform tangent, full-storage assembled operator)");
     if (cfg->material == MACROC_MAT_PER_GP && cfg->op == MACROC_OP_MATRIX_FREE)
         FAIL((macroc_ctx *)nullptr, MACROC_ERR_UNSUPPORTED, "macroc_create: per-Gauss-point tangents need an assembled operator");
     int ndev = 0;
@@ -535,6 +605,8 @@ extern "C" int macroc_create(const macroc_config *cfg, int rank, int nranks, con
         memcpy(&id, id128, 128);
         ncclResult_t e = ncclCommInitRank(&c->comm, nranks, id, rank);
         if (e != ncclSuccess) { g_last_error = std::string("ncclCommInitRank -> ") + ncclGetErrorString(e); ctx_free(c); return MACROC_ERR_NCCL; }
+        int mrc = mbox_setup(c);
+        if (mrc) { ctx_free(c); return mrc; }
     }
 #undef CUC
     *out = c;
@@ -858,7 +930,8 @@ static int residual_launch(macroc_ctx *c, int *nparts_out)
         const int l0 = lay_lo - c->er.ezs, nl = lay_hi - lay_lo + 1;
         if (nl > 0) {
             int64_t n = (int64_t)s.lnex * s.lney * nl;
-            if (per_gp) LAUNCH(c, k_elem_forces<true>, cdiv64(n, 128), 128, g, c->er, l0, nl, c->geo.wg, c->vec[V_U], c->stress, c->scratch);
+            if (c->cfg.strict_fp) LAUNCH(c, k_elem_forces_strict, cdiv64(n, 128), 128, g, c->er, l0, nl, c->geo.wg, c->vec[V_U], c->scratch);
+            else if (per_gp) LAUNCH(c, k_elem_forces<true>, cdiv64(n, 128), 128, g, c->er, l0, nl, c->geo.wg, c->vec[V_U], c->stress, c->scratch);
             else LAUNCH(c, k_elem_forces<false>, cdiv64(n, 128), 128, g, c->er, l0, nl, c->geo.wg, c->vec[V_U], c->stress, c->scratch);
         }
         int blocks = cdiv64(g.npl * nk, 256);
@@ -878,7 +951,8 @@ extern "C" int macroc_assembly_res(macroc_ctx *c, double *norm)
     int nparts = 0;
     int rc = residual_launch(c, &nparts);
     if (rc) return rc;
-    LAUNCH(c, k_reduce, 1, 256, c->partial, nparts, c->sums);
+    if (c->cfg.strict_fp) LAUNCH(c, k_seq_norm2, 1, 32, c->g, c->vec[V_B], c->sums);     // the sequential Vec's summation order
+    else LAUNCH(c, k_reduce, 1, 256, c->partial, nparts, c->sums);
     rc = allreduce_sums(c, 1);
     if (rc) return rc;
     CU(c, cudaMemcpyAsync(c->sums_host, c->sums, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
@@ -1020,14 +1094,28 @@ static int spmv_sym_launch(macroc_ctx *c, double *p, double *w, int first, int c
         if (e1 != cudaSuccess || e2 != cudaSuccess) return -1;
         configured[c->device & 63] = true;
     }
+    // Work items = bands (x tile x R rows) x z segments; one item per resident warp is the goal.
+    // Cost model (tile loads, relative): a warp's items run back to back, an item streams R rows of
+    // lseg planes plus the scatter-only pass below it (5 of 7 chunks), and re-reads (9/13 of the)
+    // neighbour blocks of the rows above / below the band: pick the (R, nseg) with the cheapest
+    // slowest warp; 256^3 lands on R = 7, nseg = 4 -> exactly 148 x 8 items.
     const int64_t target = (int64_t)148 * WARPS;
-    int R = c->sym_R > 0 ? c->sym_R : (int)std::min<int64_t>(RMAX, std::max<int64_t>(1, (int64_t)c->sg.rt * g.NY * count / target));
-    R = std::max(1, std::min({R, RMAX, g.NY}));
+    int R = 1, nseg = 1;
+    {
+        double best = 1e300;
+        const int r_lo = c->sym_R > 0 ? std::min(c->sym_R, RMAX) : 1, r_hi = c->sym_R > 0 ? r_lo : std::min(RMAX, g.NY);
+        for (int r = r_hi; r >= r_lo; --r) {
+            const int64_t bnds = (int64_t)c->sg.rt * ((g.NY + r - 1) / r);
+            const int s_hi = c->sym_nseg > 0 ? c->sym_nseg : (int)std::min<int64_t>(count, 4 * target / bnds + 1);
+            for (int sgm = c->sym_nseg > 0 ? c->sym_nseg : 1; sgm <= s_hi; ++sgm) {
+                const int ls = (count + sgm - 1) / sgm, eff = (count + ls - 1) / ls;
+                const int64_t waves = (bnds * eff + target - 1) / target;
+                const double cost = (double)waves * r * (ls + 0.7) * (1. + 0.64 / r);
+                if (cost < best * (1. - 1e-9)) { best = cost; R = r; nseg = eff; }
+            }
+        }
+    }
     const int64_t bands = (int64_t)c->sg.rt * ((g.NY + R - 1) / R);
-    int nseg = c->sym_nseg > 0 ? c->sym_nseg : (int)std::max<int64_t>(1, target / bands);
-    nseg = std::min(nseg, count);
-    const int lseg = (count + nseg - 1) / nseg;
-    nseg = (count + lseg - 1) / lseg;                 // drop empty segments
     const int blocks = (int)std::min<int64_t>(cdiv64(bands * nseg, WARPS), 148);
     if (with_dot) k_spmv_sym<WARPS, NSTAGE, RMAX, true><<<blocks, WARPS * 32, SM::total, c->stream>>>(g, c->sg, c->Asym, p, w, first, first + count, R, nseg, partial, done, c->sym_hint);
     else k_spmv_sym<WARPS, NSTAGE, RMAX, false><<<blocks, WARPS * 32, SM::total, c->stream>>>(g, c->sg, c->Asym, p, w, first, first + count, R, nseg, partial, done, c->sym_hint);
@@ -1038,7 +1126,7 @@ static int spmv_sym_launch(macroc_ctx *c, double *p, double *w, int first, int c
 // w = A p on the context's stream; p's halo is exchanged on comm_stream while
 // the rows that do not touch a ghost plane are computed.
 static int apply_operator(macroc_ctx *c, int op, double *p, double *w, bool with_dot, const int *done,
-                          bool fuse_pw_scalars = false)
+                          bool fuse_pw_scalars = false, int *nparts_out = nullptr)
 {
     const GridDev &g = c->g;
     const bool comm = has_comm(c);
@@ -1082,8 +1170,9 @@ static int apply_operator(macroc_ctx *c, int op, double *p, double *w, bool with
                 case 4: blocks = spmv_sym_launch<6, 4, 10>(c, p, w, (int)first, (int)count, c->partial + nparts, with_dot, done); break;
                 case 5: blocks = spmv_sym_launch<8, 3, 10>(c, p, w, (int)first, (int)count, c->partial + nparts, with_dot, done); break;
                 case 6: blocks = spmv_sym_launch<4, 6, 32>(c, p, w, (int)first, (int)count, c->partial + nparts, with_dot, done); break;
-                case 7: blocks = spmv_sym_launch<4, 5, 32>(c, p, w, (int)first, (int)count, c->partial + nparts, with_dot, done); break;
-                default: blocks = spmv_sym_launch<8, 3, 16>(c, p, w, (int)first, (int)count, c->partial + nparts, with_dot, done); break;
+                case 8: blocks = spmv_sym_launch<8, 3, 16>(c, p, w, (int)first, (int)count, c->partial + nparts, with_dot, done); break;
+                // default: 8 warps x 3 ring stages, bands of up to 8 rows: 168 KB of shared memory leave 32 KB of L1 for p
+                default: blocks = spmv_sym_launch<8, 3, 8>(c, p, w, (int)first, (int)count, c->partial + nparts, with_dot, done); break;
             }
             if (blocks < 0) { rc_run = MACROC_ERR_CUDA; return; }
         } else if (mf) {
@@ -1117,25 +1206,48 @@ static int apply_operator(macroc_ctx *c, int op, double *p, double *w, bool with
         run(0, total);
     if (rc_run) FAIL(c, rc_run, "apply_operator: kernel configuration failed (shared memory)");
     if (with_dot) {
-        if (fuse_pw_scalars) LAUNCH(c, k_cg_reduce_pw, 1, 256, c->partial, nparts, c->sc);
+        if (nparts_out) *nparts_out = nparts;        // the caller folds the partials (mailbox all-reduce kernel)
+        else if (fuse_pw_scalars) LAUNCH(c, k_cg_reduce_pw, 1, 256, c->partial, nparts, c->sc);
         else LAUNCH(c, k_reduce, 1, 256, c->partial, nparts, c->sums);
     }
     CU(c, cudaGetLastError());
     return MACROC_OK;
 }
 
+// one PCG iteration with the reference's rounding (strict_fp.cuh)
+static int cg_iteration_strict(macroc_ctx *c)
+{
+    const GridDev &g = c->g;
+    const int nbk = cdiv64(g.nloc, 256);
+    LAUNCH(c, k_cg_update_p_strict, nbk, 256, g, c->sc, c->vec[V_R], c->vec[V_DINV], c->vec[V_P]);
+    LAUNCH(c, k_spmv_strict, nbk, 256, g, c->A, c->vec[V_P], c->vec[V_W]);
+    LAUNCH(c, k_seq_dots, 1, 32, g, 0, c->vec[V_P], c->vec[V_W], c->sums);
+    LAUNCH(c, k_cg_scalars_pw, 1, 1, c->sc, c->sums);
+    LAUNCH(c, k_cg_update_xr_strict, nbk, 256, g, c->sc, c->vec[V_P], c->vec[V_W], c->vec[V_DU], c->vec[V_R]);
+    LAUNCH(c, k_seq_dots, 1, 32, g, 1, c->vec[V_R], c->vec[V_DINV], c->sums);
+    LAUNCH(c, k_cg_scalars_iter, 1, 1, c->sc, c->sums);
+    CU(c, cudaGetLastError());
+    return MACROC_OK;
+}
+
 static int cg_iteration(macroc_ctx *c, int op)
 {
+    if (c->cfg.strict_fp) return cg_iteration_strict(c);
     const GridDev &g = c->g;
     const int nb = c->vec_blocks;
     LAUNCH(c, k_cg_update_p, nb, 256, g, c->sc, c->vec[V_R], c->vec[V_DINV], c->vec[V_P]);
     const bool sample = c->prof_on && c->prof_used < macroc_ctx::PROF_RING && (c->prof_counter++ % c->prof_stride) == 0;
     if (sample) CU(c, cudaEventRecord(c->prof_ev[2 * c->prof_used], c->stream));
     const bool single = !has_comm(c);            // no all-reduce between reduction and scalar update
-    int rc = apply_operator(c, op, c->vec[V_P], c->vec[V_W], true, &c->sc->done, single);
+    const MboxDev mb = {c->mbox_peers, c->slab.rank, c->slab.nranks};
+    int nparts = 0;
+    int rc = apply_operator(c, op, c->vec[V_P], c->vec[V_W], true, &c->sc->done, single, c->mbox_on ? &nparts : nullptr);
     if (rc) return rc;
     if (sample) { CU(c, cudaEventRecord(c->prof_ev[2 * c->prof_used + 1], c->stream)); c->prof_used++; }
-    if (!single) {
+    if (c->mbox_on) {
+        // partials -> mailboxes of all ranks -> rank-ordered sum -> CG scalars, one launch
+        LAUNCH(c, k_cg_reduce_pw_mbox, 1, 256, c->partial, nparts, c->sc, mb, ++c->mbox_seq);
+    } else if (!single) {
         rc = allreduce_sums(c, 1);
         if (rc) return rc;
         LAUNCH(c, k_cg_scalars_pw, 1, 1, c->sc, c->sums);
@@ -1143,6 +1255,8 @@ static int cg_iteration(macroc_ctx *c, int op)
     LAUNCH(c, k_cg_update_xr, nb, 256, g, c->sc, c->vec[V_P], c->vec[V_W], c->vec[V_DINV], c->vec[V_DU], c->vec[V_R], c->partial, nb);
     if (single) {
         LAUNCH(c, k_cg_reduce_iter, 1, 256, c->partial, nb, c->sc);
+    } else if (c->mbox_on) {
+        LAUNCH(c, k_cg_reduce_iter_mbox, 1, 256, c->partial, nb, c->sc, mb, ++c->mbox_seq);
     } else {
         LAUNCH(c, k_reduce2, 1, 256, c->partial, nb, c->sums);
         rc = allreduce_sums(c, 2);
@@ -1161,7 +1275,18 @@ static int cg_begin(macroc_ctx *c, double rtol, double abstol, double dtol, int 
     h.rtol = rtol; h.abstol = abstol; h.dtol = dtol; h.maxits = maxits;
     c->sc_host[0] = h;
     CU(c, cudaMemcpyAsync(c->sc, &c->sc_host[0], sizeof(CgScalars), cudaMemcpyHostToDevice, c->stream));
+    if (c->cfg.strict_fp) {
+        LAUNCH(c, k_cg_init_strict, cdiv64(g.nloc, 256), 256, g, c->vec[V_B], c->vec[V_DU], c->vec[V_R]);
+        LAUNCH(c, k_seq_dots, 1, 32, g, 1, c->vec[V_R], c->vec[V_DINV], c->sums);
+        LAUNCH(c, k_cg_scalars_init, 1, 1, c->sc, c->sums);
+        return MACROC_OK;
+    }
     LAUNCH(c, k_cg_init, nb, 256, g, c->vec[V_B], c->vec[V_DINV], c->vec[V_DU], c->vec[V_R], c->partial, nb);
+    if (c->mbox_on) {
+        const MboxDev mb = {c->mbox_peers, c->slab.rank, c->slab.nranks};
+        LAUNCH(c, k_cg_reduce_init_mbox, 1, 256, c->partial, nb, c->sc, mb, ++c->mbox_seq);
+        return MACROC_OK;
+    }
     LAUNCH(c, k_reduce2, 1, 256, c->partial, nb, c->sums);
     int rc = allreduce_sums(c, 2);
     if (rc) return rc;
@@ -1190,7 +1315,7 @@ extern "C" int macroc_solve_Ax(macroc_ctx *c, int *its, double *rnorm)
     // Launch-bound small grids (BASELINE configs[1]): after the first batch, `check` iterations are
     // replayed as one CUDA graph (all kernel arguments are iteration-invariant: the CG state lives
     // on the device).  Single rank only; not while the live profile brackets launches with events.
-    const bool use_graph = !has_comm(c) && !c->prof_on && c->g.nloc <= ((int64_t)1 << 21);
+    const bool use_graph = !has_comm(c) && !c->cfg.strict_fp && !c->prof_on && c->g.nloc <= ((int64_t)1 << 21);
     for (int it = 0; it < c->cfg.ksp_maxits + 1 && !finished; ++it) {
         if (use_graph && it >= check && it % check == 0) {
             if (!c->cg_graph[op]) {
@@ -1244,6 +1369,8 @@ extern "C" int macroc_solve_Ax(macroc_ctx *c, int *its, double *rnorm)
     if (its) *its = c->sc_host[0].its;
     if (rnorm) *rnorm = c->sc_host[0].dp;       // KSPGetResidualNorm: last preconditioned norm
     c->ksp_reason = c->sc_host[0].reason;
+    if (c->ksp_reason == KSP_DIVERGED_COMM)
+        FAIL(c, MACROC_ERR_NCCL, "solve_Ax: a rank did not deliver its part of a CG dot product (mailbox all-reduce timed out)");
     return MACROC_OK;
 }
 
@@ -1252,6 +1379,8 @@ extern "C" int macroc_set_operator(macroc_ctx *c, int op)
     if (!c || (op != MACROC_OP_ASSEMBLED && op != MACROC_OP_MATRIX_FREE && op != MACROC_OP_ASSEMBLED_SYM)) return MACROC_ERR_ARG;
     if (op == MACROC_OP_MATRIX_FREE && c->cfg.material != MACROC_MAT_UNIFORM)
         FAIL(c, MACROC_ERR_UNSUPPORTED, "matrix-free operator needs the uniform tangent");
+    if (c->cfg.strict_fp && op != MACROC_OP_ASSEMBLED)
+        FAIL(c, MACROC_ERR_UNSUPPORTED, "strict_fp needs the full-storage assembled operator");
     c->cfg.op = op;
     return MACROC_OK;
 }

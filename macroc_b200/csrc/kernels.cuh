@@ -770,16 +770,20 @@ k_cg_init(GridDev g, const double *__restrict__ b, const double *__restrict__ di
 
 // scalar bookkeeping after the initial residual (KSPSolve_CG prologue +
 // KSPConvergedDefault at it 0)
-__global__ void k_cg_scalars_init(CgScalars *s, const double *sums /* zz, zr */)
+__device__ __forceinline__ void cg_scalars_init_body(CgScalars *s, double zz, double zr)
 {
-    double dp = sqrt(sums[0]);
+    double dp = sqrt(zz);
     s->dp = s->dp0 = dp;
     s->ttol = fmax(s->rtol * dp, s->abstol);
-    s->beta = sums[1]; s->betaold = 1.;
+    s->beta = zr; s->betaold = 1.;
     s->its = 0; s->done = 0; s->reason = 0;
-    if (!isfinite(dp) || !isfinite(sums[1])) { s->done = 1; s->reason = -9; }        // KSPCheckNorm / KSPCheckDot
+    if (!isfinite(dp) || !isfinite(zr)) { s->done = 1; s->reason = -9; }             // KSPCheckNorm / KSPCheckDot
     else if (dp <= s->ttol) { s->done = 1; s->reason = dp <= s->abstol ? 3 : 2; }
     else if (s->beta == 0.) { s->its = 1; s->done = 1; s->reason = 3; }
+}
+__global__ void k_cg_scalars_init(CgScalars *s, const double *sums /* zz, zr */)
+{
+    cg_scalars_init_body(s, sums[0], sums[1]);
 }
 
 // p = z + (beta/betaold) p   (first iteration: p = z), z = r*dinv recomputed

@@ -322,6 +322,25 @@ k_spmv_sym(GridDev g, SymGeom sg, const double2 *__restrict__ A, const double *_
         // the first step of the item gathers already (no scatter-only pass below): stage it now
         if (!pre && edge_lane) edge_stage(y0, z0);
         int64_t q = 0;
+        // vector operands are fetched well ahead of their use (the mbarrier wait is a scheduling fence,
+        // loads issued after it would expose their L2 latency): the operands of the first two chunks of
+        // a step are loaded at the end of the previous step, the rest two chunks ahead.
+        // load_xv(q0, ch) reads the operands of chunk ch's two slots of the node whose p is at q0.
+        auto load_xv = [&](const double *q0, int ch, double (&xq)[2][3]) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int slot = 13 + 2 * ch + h;
+                const int ddx = slot % 3 - 1, ddy = (slot / 3) % 3 - 1, ddz = slot / 9 - 1;
+                const int64_t off = ddx + NX * ddy + npl * ddz;
+                xq[h][0] = ldg_f64_hint(q0 + off, ppol); xq[h][1] = ldg_f64_hint(q0 + g.S + off, ppol); xq[h][2] = ldg_f64_hint(q0 + 2 * g.S + off, ppol);
+            }
+        };
+        double xa[2][3], xb[2][3];                                   // operands of the next two chunks to be processed
+        {
+            const double *q0 = p + g.G + x + NX * y0 + npl * (int64_t)zfirst;
+            if (pre) { load_xv(q0, SYM_PRE_CH0, xa); load_xv(q0, SYM_PRE_CH0 + 1, xb); }
+            else { load_xv(q0, 0, xa); load_xv(q0, 1, xb); }
+        }
         for (int z = zfirst; z < z1; ++z) {
             const bool scatter_only = z < z0;
             double carry0 = 0., carry1 = 0., carry2 = 0.;            // to the next row of this plane
@@ -332,7 +351,16 @@ k_spmv_sym(GridDev g, SymGeom sg, const double2 *__restrict__ A, const double *_
                 const int y = y0 + r;
                 const int64_t ln = x + NX * y + npl * z;
                 const double *p0 = p + g.G + ln, *p1 = p0 + g.S, *p2 = p1 + g.S;
-                const double pc0 = ldg_f64_hint(p0, ppol), pc1 = ldg_f64_hint(p1, ppol), pc2 = ldg_f64_hint(p2, ppol);
+                // the next step (row r+1 of this plane, or row 0 of the next plane) and where it starts
+                const bool last_row = r + 1 == rows;
+                const int zn = last_row ? z + 1 : z, yn = last_row ? y0 : y + 1;
+                const bool has_next = zn < z1;
+                const double *pn = p + g.G + x + NX * yn + npl * (int64_t)zn;
+                const int chn0 = zn < z0 ? SYM_PRE_CH0 : 0;          // first chunk of the next step
+                // the node's own p is slot 13's operand (chunk 0); a scatter-only step does not stream chunk 0
+                double pc0, pc1, pc2;
+                if (scatter_only) { pc0 = ldg_f64_hint(p0, ppol); pc1 = ldg_f64_hint(p1, ppol); pc2 = ldg_f64_hint(p2, ppol); }
+                else { pc0 = xa[0][0]; pc1 = xa[0][1]; pc2 = xa[0][2]; }
                 // what the plane below and the previous row of this plane scattered to this node
                 double a0 = acc[(r * 3 + 0) * TILE_NODES] + carry0, a1 = acc[(r * 3 + 1) * TILE_NODES] + carry1,
                        a2 = acc[(r * 3 + 2) * TILE_NODES] + carry2;
@@ -341,12 +369,7 @@ k_spmv_sym(GridDev g, SymGeom sg, const double2 *__restrict__ A, const double *_
                     cp_async_wait_all();
                     edge_apply(y, z, a0, a1, a2);
                 }
-                {
-                    // stage the next step's (r+1 of this plane, or row 0 of the next plane)
-                    const bool last_row = r + 1 == rows;
-                    const int zn = last_row ? z + 1 : z, yn = last_row ? y0 : y + 1;
-                    if (edge_lane && zn < z1 && zn >= z0) edge_stage(yn, zn);
-                }
+                if (edge_lane && has_next && zn >= z0) edge_stage(yn, zn);      // stage the next step's
                 // (1b) first / last row of the band: the rows above / below belong to another band.  Three
                 // slots (ddx = -1, 0, +1) per group, all loads of a group in flight together
                 if (!scatter_only) {
@@ -355,20 +378,6 @@ k_spmv_sym(GridDev g, SymGeom sg, const double2 *__restrict__ A, const double *_
                 }
                 // (2) own blocks (slots 13..26) from the TMA ring: row i, and the transposed use for row i + off
                 double nc0 = 0., nc1 = 0., nc2 = 0.;                 // carry for the next row
-                // vector operands of a chunk's two slots, fetched one chunk ahead of their use (the
-                // mbarrier wait is a scheduling fence: loads issued after it would expose their latency)
-                auto load_xv = [&](int ch, double (&xq)[2][3]) {
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const int slot = 13 + 2 * ch + h;
-                        const int ddx = slot % 3 - 1, ddy = (slot / 3) % 3 - 1, ddz = slot / 9 - 1;
-                        const int64_t off = ddx + NX * ddy + npl * ddz;
-                        if (slot == 13) { xq[h][0] = pc0; xq[h][1] = pc1; xq[h][2] = pc2; }
-                        else { xq[h][0] = ldg_f64_hint(p0 + off, ppol); xq[h][1] = ldg_f64_hint(p1 + off, ppol); xq[h][2] = ldg_f64_hint(p2 + off, ppol); }
-                    }
-                };
-                double xnext[2][3];
-                if (scatter_only) load_xv(SYM_PRE_CH0, xnext); else load_xv(0, xnext);
 #pragma unroll
                 for (int ch = 0; ch < SYM_CHUNKS; ++ch) {
                     if (scatter_only && ch < SYM_PRE_CH0) continue;      // warp-uniform: these chunks were not streamed
@@ -377,8 +386,15 @@ k_spmv_sym(GridDev g, SymGeom sg, const double2 *__restrict__ A, const double *_
                     ++q; ++c;
                     double xv[2][3];
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) { xv[h][0] = xnext[h][0]; xv[h][1] = xnext[h][1]; xv[h][2] = xnext[h][2]; }
-                    if (ch + 1 < SYM_CHUNKS) load_xv(ch + 1, xnext);
+                    for (int h = 0; h < 2; ++h) {
+                        xv[h][0] = xa[h][0]; xv[h][1] = xa[h][1]; xv[h][2] = xa[h][2];
+                        xa[h][0] = xb[h][0]; xa[h][1] = xb[h][1]; xa[h][2] = xb[h][2];
+                    }
+                    // two chunks ahead: still this step, or the first chunks of the next one
+                    if (ch + 2 < SYM_CHUNKS) load_xv(p0, ch + 2, xb);
+                    else if (has_next) {
+                        if (chn0 == 0) load_xv(pn, ch + 2 - SYM_CHUNKS, xb); else load_xv(pn, ch + 2 - SYM_CHUNKS + SYM_PRE_CH0, xb);
+                    }
                     mbar_wait(&bars[stage], parity);
                     const double2 *sv = reinterpret_cast<const double2 *>(ring + stage * CHUNK_BYTES) + lane;
                     double2 v[9];
