@@ -330,6 +330,7 @@ def run_gpu_arm(args):
                    ts=args.steps + args.warmup + 1, device=local_rank, op=op)
     m = M.MacroC(cfg, rank=rank, nranks=world, unique_id=uid)
     nloc = m.local_ndof
+    allreduce_path = m.allreduce_path()
     part = M.partition(cfg, rank, world)
     zs, nzl = part["corners"][2], part["corners"][5]
     zblocks = 3 * nzl - (1 if zs == 0 else 0) - (1 if zs + nzl == nz else 0)
@@ -436,11 +437,12 @@ def run_gpu_arm(args):
     # ---- BASELINE configs[4]: 512^3 strong scaling on 8 GPUs (every rank takes part) --------
     other = {}
     m.close()
-    if world == 8 and not custom and not args.no_extras:
+    c5g = int(os.environ.get("MACROC_BENCH_C5_GRID", "512" if world == 8 else "0"))   # (the variable: dry runs of this section)
+    if c5g and not custom and not args.no_extras:
         try:
-            c5 = M.MacroC(M.Config(NX=512, NY=512, NZ=512, pz=8, lx=50.0, ly=1.0, lz=50.0, bc_type=M.BC_BENDING, ts=8,
+            c5 = M.MacroC(M.Config(NX=c5g, NY=c5g, NZ=c5g, pz=world, lx=50.0, ly=1.0, lz=50.0, bc_type=M.BC_BENDING, ts=8,
                                    device=local_rank, op=op), rank=rank, nranks=world,
-                          unique_id=bcast_id())
+                          unique_id=bcast_id() if world > 1 else None)
             c5.time_step(1)
             c5.profile_enable(True, 8)
             barrier()
@@ -451,12 +453,12 @@ def run_gpu_arm(args):
             ms5 = max_over_ranks(c5.event_elapsed_ms(0, 1)) / len(rs)
             s_ms, s_its = c5.profile_get_solve()
             ap5, _ = c5.profile_get()
-            other["strong_scaling_512cube_8gpu"] = {
-                "ndof": 3 * 512 ** 3, "steps": len(rs), "ms_per_step": ms5, "value": 3 * 512 ** 3 / (ms5 * 1e-3), "unit": UNIT,
+            other["strong_scaling_512cube_8gpu" if (c5g, world) == (512, 8) else f"strong_scaling_{c5g}cube_{world}gpu"] = {
+                "ndof": 3 * c5g ** 3, "steps": len(rs), "ms_per_step": ms5, "value": 3 * c5g ** 3 / (ms5 * 1e-3), "unit": UNIT,
                 "cg_iterations_per_step": statistics.mean(sum(r["ksp_its"]) for r in rs),
                 "newton_its_per_step": [r["newton_its"] for r in rs], "operator": op_name,
                 "cg_iteration_ms": max_over_ranks(s_ms / s_its if s_its else 0.0), "operator_apply_ms": max_over_ranks(ap5),
-                "note": "BASELINE configs[4]: 512^3 nodes, -da_processors_z 8, bending BC, multi-step Newton"}
+                "note": f"BASELINE configs[4]: {c5g}^3 nodes, -da_processors_z {world}, bending BC, multi-step Newton"}
             c5.close()
         except Exception as exc:
             other["strong_scaling_512cube_8gpu"] = {"error": str(exc)}
@@ -556,7 +558,7 @@ def run_gpu_arm(args):
         "operator": {"assembled": "assembled, full 27-slot block storage", "sym": "assembled, symmetric block storage (14 of 27 slots)",
                      "matrix-free": "matrix-free 27-point stencil"}[op_name],
         "cg_iterations_per_step": its_step, "newton_its_per_step": newton, "wall_ms_per_step": wall_ms_step,
-        "cg_iteration_ms": cg_iteration_ms,
+        "cg_iteration_ms": cg_iteration_ms, "cg_allreduce": allreduce_path,
         "cg_matmult_gbps": roof.get("achieved") if op != M.OP_MATRIX_FREE else None,
         "cg_iteration_dof_per_s": nd * its_step / (ms_step * 1e-3) if its_step else None,
         "roofline": roof, "cpu_baseline": cpu_obj, "matrix_free": alt.get("matrix-free"),

@@ -206,6 +206,9 @@ int macroc_time_kernel(macroc_ctx *ctx, int what, int reps, int flush_l2, double
  * TFLOP/s: the denominator of the FP64-pipe fractions quoted for the matrix-free apply and the
  * element assembly (no FP64 figure is in MEASURED_PEAKS.json). */
 int macroc_fp64_probe(macroc_ctx *ctx, double *tflops);
+/* how the CG dot products are reduced over the ranks: 0 one rank, 1 ncclAllReduce, 2 peer-mapped
+ * mailboxes inside the reduction kernels (csrc/cg_mbox.cuh), 3 loopback host sum */
+int macroc_allreduce_path(const macroc_ctx *ctx);
 uint64_t macroc_launch_count(const macroc_ctx *ctx);       /* kernels launched so far */
 /* CUDA-event stopwatch on the context's stream (slots 0..7): record, then
  * elapsed(a, b) synchronises on b and returns the device time between them. */

@@ -37,7 +37,7 @@ EXPORTS = [
     "macroc_time_kernel", "macroc_launch_count", "macroc_device_synchronize", "macroc_version",
     "macroc_event_record", "macroc_event_elapsed_ms", "macroc_profile_enable", "macroc_profile_get",
     "macroc_homogenize", "macroc_gp_arrays", "macroc_set_gp_data", "macroc_set_operator", "macroc_write_pvtu",
-    "macroc_loopback_id", "macroc_fp64_probe", "macroc_profile_get_solve",
+    "macroc_loopback_id", "macroc_fp64_probe", "macroc_profile_get_solve", "macroc_allreduce_path",
 ]
 
 
@@ -132,6 +132,7 @@ def lib():
     L.macroc_get_strain_stress.argtypes = [vp, C.c_void_p, C.c_void_p, C.POINTER(C.c_int64)]
     L.macroc_time_kernel.argtypes = [vp, C.c_int, C.c_int, C.c_int, dp]
     L.macroc_fp64_probe.argtypes = [vp, dp]
+    L.macroc_allreduce_path.argtypes = [vp]
     L.macroc_launch_count.argtypes = [vp]; L.macroc_launch_count.restype = C.c_uint64
     L.macroc_device_synchronize.argtypes = [vp]
     L.macroc_event_record.argtypes = [vp, C.c_int]
@@ -400,6 +401,10 @@ class MacroC:
         ms = C.c_double()
         self._chk(self._L.macroc_time_kernel(self._h, what, reps, int(flush_l2), C.byref(ms)))
         return ms.value
+
+    def allreduce_path(self) -> str:
+        return {0: "none (one rank)", 1: "ncclAllReduce", 2: "peer-mapped mailboxes in the reduction kernels", 3: "loopback host sum"}.get(
+            int(self._L.macroc_allreduce_path(self._h)), "?")
 
     def fp64_probe(self) -> float:
         """Measured DFMA rate of the device in TFLOP/s (register-resident FMA chains)."""

@@ -1748,6 +1748,14 @@ extern "C" int macroc_device_synchronize(macroc_ctx *c)
     return MACROC_OK;
 }
 
+extern "C" int macroc_allreduce_path(const macroc_ctx *c)
+{
+    if (!c) return -1;
+    if (c->loop) return 3;
+    if (!c->comm) return 0;
+    return c->mbox_on ? 2 : 1;
+}
+
 extern "C" int macroc_fp64_probe(macroc_ctx *c, double *tflops)
 {
     if (!c || !tflops) return MACROC_ERR_ARG;
