@@ -342,9 +342,14 @@ static int ctx_free(macroc_ctx *c)
     cudaFree(c->mbox_peers); cudaFree(c->mbox);
     if (c->comm) ncclCommDestroy(c->comm);
     if (c->loop) {
-        // the last member to leave frees the group; a member that leaves early breaks it for the rest
+        // The last member to leave frees the group; a member that leaves early breaks it for the rest.
+        // Announcing the departure (left++) is this rank's LAST access to the group: once it is visible
+        // another thread may delete the object.
         LoopGroup *grp = c->loop;
         LoopGroup::Member &me = grp->m[(size_t)c->slab.rank];
+        if (me.ev_ready) cudaEventDestroy(me.ev_ready);
+        if (me.ev_done) cudaEventDestroy(me.ev_done);
+        me.ev_ready = me.ev_done = nullptr;
         bool last;
         {
             std::lock_guard<std::mutex> lk(grp->mu);
@@ -352,9 +357,6 @@ static int ctx_free(macroc_ctx *c)
             last = grp->left == grp->joined;
             if (!last) { grp->broken = true; grp->cv.notify_all(); }
         }
-        if (me.ev_ready) cudaEventDestroy(me.ev_ready);
-        if (me.ev_done) cudaEventDestroy(me.ev_done);
-        me.ev_ready = me.ev_done = nullptr;
         if (last) { if (grp->host_part) cudaFreeHost(grp->host_part); delete grp; }
         c->loop = nullptr;
     }

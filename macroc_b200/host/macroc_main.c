@@ -38,7 +38,7 @@ static int env_int(const char *name, int dflt)
         int _rc = (call);                                                                \
         if (_rc) {                                                                       \
             fprintf(stderr, "macroc: %s failed (%d): %s\n", #call, _rc, macroc_last_error(ctx)); \
-            return _rc;                                                                  \
+            exit(_rc ? _rc : 1);   /* the process exit tears the communicator down: peers fail instead of waiting */ \
         }                                                                                \
     } while (0)
 
@@ -55,25 +55,47 @@ int main(int argc, char **argv)
     cfg.device = env_int("LOCAL_RANK", 0);
     unsigned char id[128];
     memset(id, 0, sizeof(id));
+    const char *id_path = NULL;
     if (nranks > 1) {
-        const char *path = getenv("MACROC_ID_FILE");
+        /* The 128-byte NCCL id travels through a file (no MPI in the image).  The file also carries a
+         * per-launch nonce (MACROC_LAUNCH_NONCE, else MASTER_PORT): a file left behind by an earlier run
+         * at the same path is recognised as stale instead of sending the ranks into a hang inside
+         * ncclCommInitRank.  Rank 0 removes the file before writing (tmp + rename) and after the
+         * communicator exists. */
+        const char *path = id_path = getenv("MACROC_ID_FILE");
         if (!path) { fprintf(stderr, "macroc: WORLD_SIZE > 1 needs MACROC_ID_FILE\n"); return 62; }
+        const char *nv = getenv("MACROC_LAUNCH_NONCE") ? getenv("MACROC_LAUNCH_NONCE") : getenv("MASTER_PORT");
+        char nonce[64];
+        memset(nonce, 0, sizeof(nonce));
+        if (nv) strncpy(nonce, nv, sizeof(nonce) - 1);
         char tmp[4096];
         snprintf(tmp, sizeof(tmp), "%s.tmp", path);
         if (rank == 0) {
+            unlink(path);
             if (macroc_get_unique_id(id)) { fprintf(stderr, "macroc: %s\n", macroc_last_error(NULL)); return 99; }
             FILE *f = fopen(tmp, "wb");
-            if (!f || fwrite(id, 1, 128, f) != 128) return 65;
+            if (!f || fwrite(id, 1, 128, f) != 128 || fwrite(nonce, 1, sizeof(nonce), f) != sizeof(nonce)) {
+                fprintf(stderr, "macroc: cannot write %s\n", tmp);
+                return 65;
+            }
             fclose(f);
-            rename(tmp, path);
+            if (rename(tmp, path)) { fprintf(stderr, "macroc: cannot create %s\n", path); return 65; }
         } else {
-            FILE *f = NULL;
-            for (int tries = 0; tries < 600 && !(f = fopen(path, "rb")); ++tries) usleep(100000);
-            if (!f || fread(id, 1, 128, f) != 128) { fprintf(stderr, "macroc: cannot read %s\n", path); return 65; }
-            fclose(f);
+            int ok = 0;
+            for (int tries = 0; tries < 600 && !ok; ++tries) {
+                FILE *f = fopen(path, "rb");
+                char got[64];
+                if (f && fread(id, 1, 128, f) == 128 && fread(got, 1, sizeof(got), f) == sizeof(got) &&
+                    memcmp(got, nonce, sizeof(nonce)) == 0)
+                    ok = 1;
+                if (f) fclose(f);
+                if (!ok) usleep(100000);
+            }
+            if (!ok) { fprintf(stderr, "macroc: no NCCL id for this launch in %s (stale file or rank 0 missing)\n", path); return 65; }
         }
     }
     FILE *file_out = rank == 0 ? fopen("info.dat", "w") : NULL;
+    if (rank == 0 && !file_out) { fprintf(stderr, "macroc: cannot open info.dat for writing\n"); return 65; }
     if (rank == 0) {
         printf("\nMacroC : A HPC for FE2 Multi-scale Simulations\n\n");
         printf("Boundary Condition : %s\n", cfg.bc_type == MACROC_BC_BENDING ? "BC_BENDING" : "BC_CIRCLE");
@@ -86,6 +108,7 @@ int main(int argc, char **argv)
                cfg.ksp_dtol, cfg.ksp_maxits);
     }
     int rc = macroc_create(&cfg, rank, nranks, nranks > 1 ? id : NULL, &ctx);
+    if (rank == 0 && id_path) unlink(id_path);          /* every rank has read it once the communicator exists */
     if (rc) { fprintf(stderr, "macroc: macroc_create failed (%d): %s\n", rc, macroc_last_error(NULL)); return rc; }
     if (rank == 0)
         printf("------------------------------------------------------------\n"
