@@ -163,11 +163,13 @@ __constant__ KkInfo c_kkinfo = make_kkinfo();
 // The Gauss-point loop is fully unrolled so that every shape-function derivative of the block
 // columns is an immediate constant-bank operand of its DFMA; wg is applied once, when a thread adds
 // its 3 x 24 row block to the tile.
+constexpr int ASM_COLBLOCK = 64;
+
 template <bool PER_GP, bool SYM>
 __global__ void __launch_bounds__(256, 1)
 k_assemble_elements(GridDev g, SymGeom sg, ElemRange er, double wg, const double *__restrict__ ctan_gp,
                     const uint8_t *__restrict__ nodemask, double2 *__restrict__ A, double *__restrict__ dinv,
-                    int64_t tile_lo, int64_t tile_hi)
+                    int64_t tile_lo, int64_t tile_hi, int64_t tpp /* tiles per plane (rounded up for the full layout) */)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *tileA = reinterpret_cast<double *>(smem_raw);                  // TILE_DOUBLES, full 27-slot indexing
@@ -176,12 +178,22 @@ k_assemble_elements(GridDev g, SymGeom sg, ElemRange er, double wg, const double
     const int apx = node_px(a), apy = node_py(a), apz = node_pz(a);
     const int64_t per_layer = er.nex * er.ney;
 
-    for (int64_t tile = tile_lo + blockIdx.x; tile < tile_hi; tile += gridDim.x) {
+    // Traversal: column blocks of ASM_COLBLOCK tiles of a plane, swept through all planes before the next
+    // block.  An element's tangents are needed by the tiles of two rows and two planes; with the plain
+    // linear order the second plane comes a whole plane (150 MB of tangents + 128 MB of operator at 256^3)
+    // later and misses L2 (ncu: 81 GB read for 38 GB of tangents).  Here the CTAs in flight cover a few
+    // planes of one column block, so the second use follows the first within a few MB of traffic.
+    const int64_t ntl = tile_hi - tile_lo;
+    const int64_t mtot = (ntl + tpp - 1) / tpp, ncb = (tpp + ASM_COLBLOCK - 1) / ASM_COLBLOCK;
+    for (int64_t v = blockIdx.x; v < ncb * ASM_COLBLOCK * mtot; v += gridDim.x) {
+        const int64_t cb = v / (ASM_COLBLOCK * mtot), rem = v - cb * (ASM_COLBLOCK * mtot);
+        const int64_t col = cb * ASM_COLBLOCK + rem % ASM_COLBLOCK;
+        const int64_t tile = tile_lo + col + (rem / ASM_COLBLOCK) * tpp;
+        if (col >= tpp || tile >= tile_hi) continue;                       // block-uniform
         // node of (tile, lane): local box coordinates (i, j), slab-local plane kl, linear index ln0 of lane 0
         int i = 0, j = 0, kl = 0, nvalid = 0;
         int64_t ln0;
         if (SYM) {
-            const int64_t tpp = sym_tiles_per_plane(g, sg);
             kl = (int)((tile + tpp) / tpp) - 1;                            // floor: the ghost plane is -1
             const int64_t rem = tile - (int64_t)kl * tpp;
             j = (int)(rem / sg.rt);
@@ -193,7 +205,13 @@ k_assemble_elements(GridDev g, SymGeom sg, ElemRange er, double wg, const double
             ln0 = tile * TILE_NODES;
             const int64_t ln = ln0 + lane;
             nvalid = (int)min((int64_t)32, g.nloc - ln0);
-            if (lane < nvalid) { i = (int)(ln % g.NX); j = (int)((ln / g.NX) % g.NY); kl = (int)(ln / g.npl); }
+            // (a rank's local node count fits 31 bits: 32-bit divisions instead of 64-bit calls)
+            if (lane < nvalid) {
+                const unsigned lnu = (unsigned)ln, nx = (unsigned)g.NX, npl = (unsigned)g.npl;
+                kl = (int)(lnu / npl);
+                const unsigned inpl = lnu - (unsigned)kl * npl;
+                j = (int)(inpl / nx); i = (int)(inpl - (unsigned)j * nx);
+            }
         }
         const bool valid = lane < nvalid;
         const int k = kl + g.zs;
@@ -276,11 +294,9 @@ k_assemble_elements(GridDev g, SymGeom sg, ElemRange er, double wg, const double
         // MatZeroRowsColumns (bcs.c:341-347) + PCJACOBI diagonal + coalesced store; warp a takes the
         // entry pairs a, a+8, ...: the entry decoding (slot, row, col) is a warp-uniform table lookup
         const unsigned own = nbmask[13 * 32 + lane];
-        auto masked = [&](int kk) -> double {
-            const unsigned info = c_kkinfo.v[kk];
+        auto apply_mask = [&](unsigned info, double v) -> double {
             if (info & 0x8000u) return 0.;
             const int slot = info & 31, rr = (info >> 5) & 3, cc = (info >> 7) & 3;
-            double v = tileA[((kk >> 1) * TILE_NODES + lane) * 2 + (kk & 1)];
             const unsigned nb = nbmask[slot * 32 + lane];
             const bool isdiag = (info >> 9) & 1u;
             if (((own >> rr) & 1u) || ((nb >> cc) & 1u)) v = isdiag ? 1. : 0.;
@@ -288,17 +304,22 @@ k_assemble_elements(GridDev g, SymGeom sg, ElemRange er, double wg, const double
             if (isdiag && valid && (!SYM || kl >= 0)) dinv[rr * g.S + g.G + ln0 + lane] = v != 0. ? 1. / v : 1.;
             return v;
         };
+        // streaming stores: the operator must not push the tangents of the next plane out of L2
         if (SYM) {
             double2 *At = A + tile * (SYM_PAIRS * TILE_NODES) + lane;
             for (int pr = a; pr < SYM_PAIRS; pr += 8) {
-                const double v0 = masked(117 + 2 * pr), v1 = masked(118 + 2 * pr);
-                At[pr * TILE_NODES] = make_double2(v0, v1);
+                const int kk0 = 117 + 2 * pr;                          // odd: the pair straddles two pairs of the staging tile
+                const double v0 = apply_mask(c_kkinfo.v[kk0], tileA[((kk0 >> 1) * TILE_NODES + lane) * 2 + 1]);
+                const double v1 = apply_mask(c_kkinfo.v[kk0 + 1], tileA[(((kk0 + 1) >> 1) * TILE_NODES + lane) * 2]);
+                __stcs(At + pr * TILE_NODES, make_double2(v0, v1));
             }
         } else {
             double2 *At = A + tile * (PAIRS * TILE_NODES) + lane;
+            const unsigned *info2 = reinterpret_cast<const unsigned *>(c_kkinfo.v);      // two 16-bit entries per pair
             for (int pr = a; pr < PAIRS; pr += 8) {
-                const double v0 = masked(2 * pr), v1 = masked(2 * pr + 1);
-                At[pr * TILE_NODES] = make_double2(v0, v1);
+                const unsigned info = info2[pr];
+                const double2 t2 = *reinterpret_cast<const double2 *>(tileA + (pr * TILE_NODES + lane) * 2);
+                __stcs(At + pr * TILE_NODES, make_double2(apply_mask(info & 0xffffu, t2.x), apply_mask(info >> 16, t2.y)));
             }
         }
         __syncthreads();

@@ -979,6 +979,7 @@ static int ensure_operator_storage(macroc_ctx *c)
 template <bool SYM>
 static int launch_assemble_elements(macroc_ctx *c, bool per_gp, double2 *A, int64_t tile_lo, int64_t tile_hi)
 {
+    const int64_t tpp = SYM ? sym_tiles_per_plane(c->g, c->sg) : std::max<int64_t>(1, (c->g.npl + TILE_NODES - 1) / TILE_NODES);
     const int smem = TILE_DOUBLES * (int)sizeof(double) + 27 * 32;
     static bool configured[64] = {false};                     // function attributes are per device
     if (!configured[c->device & 63]) {
@@ -987,8 +988,8 @@ static int launch_assemble_elements(macroc_ctx *c, bool per_gp, double2 *A, int6
         configured[c->device & 63] = true;
     }
     const int blocks = (int)std::min<int64_t>(tile_hi - tile_lo, 148 * 3);
-    if (per_gp) k_assemble_elements<true, SYM><<<blocks, 256, smem, c->stream>>>(c->g, c->sg, c->er, c->geo.wg, c->ctan, c->nodemask, A, c->vec[V_DINV], tile_lo, tile_hi);
-    else k_assemble_elements<false, SYM><<<blocks, 256, smem, c->stream>>>(c->g, c->sg, c->er, c->geo.wg, c->ctan, c->nodemask, A, c->vec[V_DINV], tile_lo, tile_hi);
+    if (per_gp) k_assemble_elements<true, SYM><<<blocks, 256, smem, c->stream>>>(c->g, c->sg, c->er, c->geo.wg, c->ctan, c->nodemask, A, c->vec[V_DINV], tile_lo, tile_hi, tpp);
+    else k_assemble_elements<false, SYM><<<blocks, 256, smem, c->stream>>>(c->g, c->sg, c->er, c->geo.wg, c->ctan, c->nodemask, A, c->vec[V_DINV], tile_lo, tile_hi, tpp);
     c->launches++;
     return MACROC_OK;
 }

@@ -469,6 +469,30 @@ def test_ksp_termination_paths():
     assert rel_err(m.get_vec(M.VEC_DU), o.get_vec("du")) < 1e-10     # same 7 iterates
 
 
+def test_ksp_divergence_reasons_with_plugin_tangents():
+    """KSPSolve_CG's divergence bookkeeping with tangents a material plug-in could hand over: a NaN tangent
+    must end the solve at once with KSP_DIVERGED_NANORINF (-9) -- not after ksp_maxits no-op sweeps -- and an
+    indefinite tangent with INDEFINITE_MAT (-10) or INDEFINITE_PC (-8)."""
+    NX, NY, NZ = 6, 4, 4
+    ne = (NX - 1) * (NY - 1) * (NZ - 1)
+    D = O.isotropic_D()
+    for kind, expect in (("nan", (-9,)), ("indefinite", (-8, -10))):
+        m = M.MacroC(M.Config(NX=NX, NY=NY, NZ=NZ, bc_type=M.BC_BENDING, material=M.MAT_PER_GP, ksp_maxits=500))
+        m.apply_bc_on_u(-1e-3); m.set_strains(); m.homogenize()
+        assert m.assembly_res() > 0
+        ctan = np.tile(D.reshape(1, 1, 36), (ne, 8, 1))
+        if kind == "nan":
+            ctan[ne // 2, 3, :] = np.nan
+        else:
+            ctan = ctan.reshape(ne, 8, 6, 6) * np.array([1, 1, 1, -1, -1, -1.])[None, None, :, None]
+        m.set_gp_data(ctan=ctan)
+        m.assembly_jac()
+        its, _ = m.solve_Ax()
+        assert m.ksp_reason() in expect, (kind, m.ksp_reason(), its)
+        assert its < 500, (kind, its)
+        m.close()
+
+
 def test_named_switch_physical_B():
     """SURVEY section 9 quirk switch: B of the physical element instead of the reference's unit
     cube (assembly.c:198) -- both sides flip together and still agree."""
