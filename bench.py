@@ -541,7 +541,7 @@ def run_gpu_arm(args):
     if fp64_tflops:
         nn = nloc / 3
         ne = (nx - 1) * (ny - 1) * (nz - 1) / world
-        fp64 = {"dfma_tflops_measured": fp64_tflops, "how": "k_fp64_probe: 16 independent DFMA chains per thread, 8 CTAs/SM, best of 5"}
+        fp64 = {"dfma_tflops_measured": fp64_tflops, "how": "k_fp64_probe(_const): 16 independent DFMA chains per thread, 8 CTAs/SM, register and constant-bank multiplier, best of 2 x 5 launches"}
         if kern.get("apply_matrix_free"):
             fp64["apply_matrix_free_frac"] = 486.0 * nn / (kern["apply_matrix_free"] * 1e-3) / 1e12 / fp64_tflops
         if kern.get("jacobian_per_element"):

@@ -163,7 +163,12 @@ int macroc_ksp_reason(const macroc_ctx *ctx, int *reason);
 int macroc_set_operator(macroc_ctx *ctx, int op);
 int macroc_update_u(macroc_ctx *ctx);                      /* VecAXPY(u,1,du) main.c:79 */
 int macroc_calc_B(int gp, double *B /* [6][24] */);        /* assembly.c:195-254 (host, constants) */
-int macroc_calc_force(macroc_ctx *ctx, double *force);     /* forces.c:25-166 */
+/* forces.c:25-166.  Deviation: with the uniform tangent the Gauss-point stresses are re-evaluated from the
+ * CURRENT u (after a halo refresh); the reference reads the stresses of the last micropp_C_homogenize,
+ * i.e. of the u before the last Newton update.  The two coincide whenever the Newton loop ended on its
+ * residual test (it then breaks right after a homogenize with no update in between); they differ if it ran
+ * out of newton_max_its.  With MACROC_MAT_PER_GP the stored stresses are used, exactly like the reference. */
+int macroc_calc_force(macroc_ctx *ctx, double *force);
 
 /* One Newton loop of one time step (main.c:53-82) with the reference's
  * control flow; res_norms gets the |RES| of every iteration (n_res of them),

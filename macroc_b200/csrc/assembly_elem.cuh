@@ -163,41 +163,105 @@ __constant__ KkInfo c_kkinfo = make_kkinfo();
 // The Gauss-point loop is fully unrolled so that every shape-function derivative of the block
 // columns is an immediate constant-bank operand of its DFMA; wg is applied once, when a thread adds
 // its 3 x 24 row block to the tile.
-constexpr int ASM_COLBLOCK = 64;
+constexpr int ASM_WARPS = 12;                                             // 4 local nodes (x 2 passes) x 3 block rows
+constexpr int ASM_THREADS = ASM_WARPS * 32;
+constexpr int ASM_STAGE_OFFSET = TILE_DOUBLES * 8 + 27 * 32 + 32;          // 16-byte aligned, behind the tile and the masks
+constexpr int ASM_SMEM_UNIFORM = TILE_DOUBLES * 8 + 27 * 32;
+constexpr int ASM_SMEM_PER_GP = ASM_STAGE_OFFSET + 36 * 128 * 8;           // + one staging buffer [36][4 nodes ah][32 lanes]: 2 CTAs fit an SM
 
+// Row D of the 3 x 24 row block (B_a^T C B) of one element, one Gauss point:
+//   T[k]      = sum_r B_a[r][D] C[r][k]            -- B_a's column D has three non-zeros
+//   blk[3b+c] += T[k] B_b[k][c]                     -- B_b's row k has one or two non-zeros per node b
+// 18 + 72 FMA; the three rows of a block are three different threads, so no product is computed twice
+// and a thread holds 24 accumulators instead of 72.  ck: the tangent, C[r][k] at ck[(6 r + k) * cstride].
+template <bool PER_GP, int D, int GP>
+__device__ __forceinline__ void integrate_gp(int gp, int a, const double *__restrict__ ck, int cstride, double (&blk)[24])
+{
+    // rows of C that meet column D of B_a, and the shape-function derivative that multiplies each:
+    // D=0: (0,hx) (3,hy) (4,hz)   D=1: (1,hy) (3,hx) (5,hz)   D=2: (2,hz) (4,hx) (5,hy)
+    constexpr int R0 = D, R1 = D == 2 ? 4 : 3, R2 = D == 0 ? 4 : 5;
+    constexpr int I0 = D, I1 = D == 0 ? 1 : 0, I2 = D == 2 ? 1 : 2;
+    const int g = GP >= 0 ? GP : gp;               // GP >= 0: compile-time Gauss point (every B_b entry an immediate)
+    const double h0 = c_dsh[g][a][I0], h1 = c_dsh[g][a][I1], h2 = c_dsh[g][a][I2];
+#pragma unroll
+    for (int kc = 0; kc < 6; ++kc) {
+        const double c0 = PER_GP ? ck[(R0 * 6 + kc) * cstride] : c_D[R0 * 6 + kc];
+        const double c1 = PER_GP ? ck[(R1 * 6 + kc) * cstride] : c_D[R1 * 6 + kc];
+        const double c2 = PER_GP ? ck[(R2 * 6 + kc) * cstride] : c_D[R2 * 6 + kc];
+        const double T = fma(h2, c2, fma(h1, c1, h0 * c0));
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+            const double bx = c_dsh[g][b][0], by = c_dsh[g][b][1], bz = c_dsh[g][b][2];
+            // row kc of B_b: (0: c0=bx) (1: c1=by) (2: c2=bz) (3: c0=by, c1=bx) (4: c0=bz, c2=bx) (5: c1=bz, c2=by)
+            if (kc == 0) blk[3 * b + 0] = fma(T, bx, blk[3 * b + 0]);
+            if (kc == 1) blk[3 * b + 1] = fma(T, by, blk[3 * b + 1]);
+            if (kc == 2) blk[3 * b + 2] = fma(T, bz, blk[3 * b + 2]);
+            if (kc == 3) { blk[3 * b + 0] = fma(T, by, blk[3 * b + 0]); blk[3 * b + 1] = fma(T, bx, blk[3 * b + 1]); }
+            if (kc == 4) { blk[3 * b + 0] = fma(T, bz, blk[3 * b + 0]); blk[3 * b + 2] = fma(T, bx, blk[3 * b + 2]); }
+            if (kc == 5) { blk[3 * b + 1] = fma(T, bz, blk[3 * b + 1]); blk[3 * b + 2] = fma(T, by, blk[3 * b + 2]); }
+        }
+    }
+}
+
+// uniform tangent: all eight Gauss points unrolled
+template <int D>
+__device__ __forceinline__ void integrate_uniform(int a, double (&blk)[24])
+{
+    integrate_gp<false, D, 0>(0, a, nullptr, 0, blk); integrate_gp<false, D, 1>(1, a, nullptr, 0, blk);
+    integrate_gp<false, D, 2>(2, a, nullptr, 0, blk); integrate_gp<false, D, 3>(3, a, nullptr, 0, blk);
+    integrate_gp<false, D, 4>(4, a, nullptr, 0, blk); integrate_gp<false, D, 5>(5, a, nullptr, 0, blk);
+    integrate_gp<false, D, 6>(6, a, nullptr, 0, blk); integrate_gp<false, D, 7>(7, a, nullptr, 0, blk);
+}
+
+// General Jacobian assembly (assembly.c:85-108 with a tangent per Gauss point).  One CTA of 12 warps per
+// operator tile, two CTAs per SM: warp (ah, d), lane = node; in pass p the thread integrates row d of the
+// 3 x 24 row block of the element in which its node is local node a = ah + 4 p (24 accumulators, 720 FMA),
+// then the 12 warps add their rows into the tile in shared memory in 8 conflict-free rounds (round b: block
+// column b; distinct (a, d) hit distinct entries).  After both passes the Dirichlet mask is applied -- tiles
+// with no Dirichlet dof in reach, the vast majority, skip it -- and the tile leaves as one contiguous store.
+// The second CTA of the SM integrates while this one reduces and stores.  Per-Gauss-point tangents are
+// staged through shared memory per Gauss point (cp.async; the three row threads of a node share one copy).
+// SYM: the tile is a row tile of the symmetric layout (spmv_sym.cuh) and only the slots 13..26 are
+// stored -- the tangent must then be symmetric (Ke is; the reference never relies on it, MATAIJ stores
+// both halves).  wg is applied once, when a thread adds its row to the tile.
 template <bool PER_GP, bool SYM>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(ASM_THREADS, 2)
 k_assemble_elements(GridDev g, SymGeom sg, ElemRange er, double wg, const double *__restrict__ ctan_gp,
                     const uint8_t *__restrict__ nodemask, double2 *__restrict__ A, double *__restrict__ dinv,
-                    int64_t tile_lo, int64_t tile_hi, int64_t tpp /* tiles per plane (rounded up for the full layout) */)
+                    int64_t tile_lo, int64_t tile_hi, int64_t tpp /* tiles per plane (rounded up for the full layout) */,
+                    int64_t colblock /* tiles of a plane per traversal block (tpp: plain linear order) */, int stream_stores)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double *tileA = reinterpret_cast<double *>(smem_raw);                  // TILE_DOUBLES, full 27-slot indexing
+    // staging tile: entry kk = slot*9 + 3 r + c of node `lane` at tileA[kk*32 + lane] -- lanes 8 bytes apart, so
+    // the read-modify-write rounds are bank-conflict free (the operator's own pair-interleaved layout is
+    // produced by the final pass)
+    double *tileA = reinterpret_cast<double *>(smem_raw);                  // 244 x 32 doubles = TILE_DOUBLES
     uint8_t *nbmask = smem_raw + TILE_DOUBLES * sizeof(double);            // [27][32]
-    const int lane = threadIdx.x & 31, a = threadIdx.x >> 5;
-    const int apx = node_px(a), apy = node_py(a), apz = node_pz(a);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ah = warp / 3, d = warp - 3 * ah;
     const int64_t per_layer = er.nex * er.ney;
+    // staging of the tangents (PER_GP): [36 entries][ah][lane]; thread (ah, d, lane) copies the entries
+    // 12 d .. 12 d + 11 of its element and reads the 18 its row needs after the barrier
+    double *stage = reinterpret_cast<double *>(smem_raw + ASM_STAGE_OFFSET) + ah * 32 + lane;
 
-    // Traversal: column blocks of ASM_COLBLOCK tiles of a plane, swept through all planes before the next
-    // block.  An element's tangents are needed by the tiles of two rows and two planes; with the plain
-    // linear order the second plane comes a whole plane (150 MB of tangents + 128 MB of operator at 256^3)
-    // later and misses L2 (ncu: 81 GB read for 38 GB of tangents).  Here the CTAs in flight cover a few
-    // planes of one column block, so the second use follows the first within a few MB of traffic.
+    // Traversal: column blocks of `colblock` tiles of a plane, swept through all planes before the next
+    // block (an element's tangents are needed by the tiles of two rows and two planes: the second plane
+    // then follows within a few MB of traffic instead of a whole plane later).
     const int64_t ntl = tile_hi - tile_lo;
-    const int64_t mtot = (ntl + tpp - 1) / tpp, ncb = (tpp + ASM_COLBLOCK - 1) / ASM_COLBLOCK;
-    for (int64_t v = blockIdx.x; v < ncb * ASM_COLBLOCK * mtot; v += gridDim.x) {
-        const int64_t cb = v / (ASM_COLBLOCK * mtot), rem = v - cb * (ASM_COLBLOCK * mtot);
-        const int64_t col = cb * ASM_COLBLOCK + rem % ASM_COLBLOCK;
-        const int64_t tile = tile_lo + col + (rem / ASM_COLBLOCK) * tpp;
+    const int64_t mtot = (ntl + tpp - 1) / tpp, ncb = (tpp + colblock - 1) / colblock;
+    for (int64_t v = blockIdx.x; v < ncb * colblock * mtot; v += gridDim.x) {
+        const int64_t cb = v / (colblock * mtot), rem = v - cb * (colblock * mtot);
+        const int64_t col = cb * colblock + rem % colblock;
+        const int64_t tile = tile_lo + col + (rem / colblock) * tpp;
         if (col >= tpp || tile >= tile_hi) continue;                       // block-uniform
         // node of (tile, lane): local box coordinates (i, j), slab-local plane kl, linear index ln0 of lane 0
         int i = 0, j = 0, kl = 0, nvalid = 0;
         int64_t ln0;
         if (SYM) {
             kl = (int)((tile + tpp) / tpp) - 1;                            // floor: the ghost plane is -1
-            const int64_t rem = tile - (int64_t)kl * tpp;
-            j = (int)(rem / sg.rt);
-            const int x0 = (int)(rem % sg.rt) * 32;
+            const int64_t rem2 = tile - (int64_t)kl * tpp;
+            j = (int)(rem2 / sg.rt);
+            const int x0 = (int)(rem2 % sg.rt) * 32;
             i = x0 + lane;
             nvalid = min(32, g.NX - x0);
             ln0 = x0 + (int64_t)g.NX * j + g.npl * kl;
@@ -215,111 +279,110 @@ k_assemble_elements(GridDev g, SymGeom sg, ElemRange er, double wg, const double
         }
         const bool valid = lane < nvalid;
         const int k = kl + g.zs;
-        for (int q = threadIdx.x; q < TILE_DOUBLES; q += blockDim.x) tileA[q] = 0.;
+        {
+            double2 *z2 = reinterpret_cast<double2 *>(tileA);
+            for (int q = threadIdx.x; q < TILE_DOUBLES / 2; q += blockDim.x) z2[q] = make_double2(0., 0.);
+        }
+        unsigned anymask = 0;
         for (int q = threadIdx.x; q < 27 * 32; q += blockDim.x) {
             const int slot = q >> 5, l2 = q & 31;
             const int ddx = slot % 3 - 1, ddy = (slot / 3) % 3 - 1, ddz = slot / 9 - 1;
             // (the ghost plane of the symmetric layout would look two planes below the slab)
             const int64_t idx = g.G + ln0 + l2 + ddx + (int64_t)g.NX * ddy + g.npl * ddz;
-            nbmask[q] = (l2 < nvalid && idx >= 0 && idx < g.S) ? nodemask[idx] : 0;
+            const uint8_t mk = (l2 < nvalid && idx >= 0 && idx < g.S) ? nodemask[idx] : 0;
+            nbmask[q] = mk;
+            anymask |= mk;
         }
-        // the element in which this node is local node a (it must be one whose tangents this rank holds)
-        const int ei = i - apx, ej = j - apy, ek = k - apz;
-        const bool exists = valid && ei >= 0 && ei < g.NX - 1 && ej >= 0 && ej < g.NY - 1 && ek >= 0 && ek < g.NZ - 1 &&
-                            ek >= er.ezs && ek < er.ezs + er.nez_ext;
-        double blk[3][24];
+        // does any node of the tile, or any of its neighbours, carry a Dirichlet dof?  (block-uniform)
+        const int masked_tile = __syncthreads_or(anymask != 0);          // also: the tile is zeroed, the masks are in
+#pragma unroll 1
+        for (int pass = 0; pass < 2; ++pass) {
+            const int a = ah + 4 * pass;
+            const int apx = node_px(a), apy = node_py(a), apz = node_pz(a);
+            // the element in which this node is local node a (it must be one whose tangents this rank holds)
+            const int ei = i - apx, ej = j - apy, ek = k - apz;
+            const bool exists = valid && ei >= 0 && ei < g.NX - 1 && ej >= 0 && ej < g.NY - 1 && ek >= 0 && ek < g.NZ - 1 &&
+                                ek >= er.ezs && ek < er.ezs + er.nez_ext;
+            double blk[24];
 #pragma unroll
-        for (int d = 0; d < 3; ++d)
+            for (int q = 0; q < 24; ++q) blk[q] = 0.;
+            if (PER_GP) {
+                const double *cg = exists ? ctan_gp + ((int64_t)(ek - er.ezs) * per_layer + ei + er.nex * (int64_t)ej) : nullptr;
+#pragma unroll 1
+                for (int gp = 0; gp < 8; ++gp) {
+                    if (exists) {                                        // this thread's third of the 36 entries
+                        double *dst = stage + (12 * d) * 128;
+                        const double *src = cg + (int64_t)(gp * 36 + 12 * d) * er.ne_ext;
 #pragma unroll
-            for (int q = 0; q < 24; ++q) blk[d][q] = 0.;
-        if (exists) {
-            const double *cg = PER_GP ? ctan_gp + ((int64_t)(ek - er.ezs) * per_layer + ei + er.nex * (int64_t)ej) : nullptr;
-            // uniform tangent: fully unrolled (every B entry an immediate operand).  Per-Gauss-point
-            // tangents: one Gauss point per loop trip -- unrolled, the 288 loads of a thread serialise
-            // behind the register allocator (measured 84 ms against 67 ms at 256^3)
-#pragma unroll (PER_GP ? 1 : 8)
-            for (int gp = 0; gp < 8; ++gp) {
-                const double hx = c_dsh[gp][a][0], hy = c_dsh[gp][a][1], hz = c_dsh[gp][a][2];
-                // stream the tangent one column k at a time: T[d] = (B_a^T C)[d][k], then every block
-                // column b takes T[d] * B_b[k][.]  (B has at most two non-zeros per (k, b))
-#pragma unroll
-                for (int kc = 0; kc < 6; ++kc) {
-                    double ck[6];
-#pragma unroll
-                    for (int r = 0; r < 6; ++r) ck[r] = PER_GP ? __ldg(cg + (int64_t)(gp * 36 + r * 6 + kc) * er.ne_ext) : c_D[r * 6 + kc];
-                    const double T0 = fma(hz, ck[4], fma(hy, ck[3], hx * ck[0]));
-                    const double T1 = fma(hz, ck[5], fma(hx, ck[3], hy * ck[1]));
-                    const double T2 = fma(hy, ck[5], fma(hx, ck[4], hz * ck[2]));
-#pragma unroll
-                    for (int b = 0; b < 8; ++b) {
-                        const double bx = c_dsh[gp][b][0], by = c_dsh[gp][b][1], bz = c_dsh[gp][b][2];
-                        // column 3b+c of B: row k non-zero for (k,c) in {(0,0),(1,1),(2,2),(3,0)=by,(3,1)=bx,(4,0)=bz,(4,2)=bx,(5,1)=bz,(5,2)=by}
-                        if (kc == 0) { blk[0][3 * b + 0] = fma(T0, bx, blk[0][3 * b + 0]); blk[1][3 * b + 0] = fma(T1, bx, blk[1][3 * b + 0]); blk[2][3 * b + 0] = fma(T2, bx, blk[2][3 * b + 0]); }
-                        if (kc == 1) { blk[0][3 * b + 1] = fma(T0, by, blk[0][3 * b + 1]); blk[1][3 * b + 1] = fma(T1, by, blk[1][3 * b + 1]); blk[2][3 * b + 1] = fma(T2, by, blk[2][3 * b + 1]); }
-                        if (kc == 2) { blk[0][3 * b + 2] = fma(T0, bz, blk[0][3 * b + 2]); blk[1][3 * b + 2] = fma(T1, bz, blk[1][3 * b + 2]); blk[2][3 * b + 2] = fma(T2, bz, blk[2][3 * b + 2]); }
-                        if (kc == 3) {
-                            blk[0][3 * b + 0] = fma(T0, by, blk[0][3 * b + 0]); blk[1][3 * b + 0] = fma(T1, by, blk[1][3 * b + 0]); blk[2][3 * b + 0] = fma(T2, by, blk[2][3 * b + 0]);
-                            blk[0][3 * b + 1] = fma(T0, bx, blk[0][3 * b + 1]); blk[1][3 * b + 1] = fma(T1, bx, blk[1][3 * b + 1]); blk[2][3 * b + 1] = fma(T2, bx, blk[2][3 * b + 1]);
-                        }
-                        if (kc == 4) {
-                            blk[0][3 * b + 0] = fma(T0, bz, blk[0][3 * b + 0]); blk[1][3 * b + 0] = fma(T1, bz, blk[1][3 * b + 0]); blk[2][3 * b + 0] = fma(T2, bz, blk[2][3 * b + 0]);
-                            blk[0][3 * b + 2] = fma(T0, bx, blk[0][3 * b + 2]); blk[1][3 * b + 2] = fma(T1, bx, blk[1][3 * b + 2]); blk[2][3 * b + 2] = fma(T2, bx, blk[2][3 * b + 2]);
-                        }
-                        if (kc == 5) {
-                            blk[0][3 * b + 1] = fma(T0, bz, blk[0][3 * b + 1]); blk[1][3 * b + 1] = fma(T1, bz, blk[1][3 * b + 1]); blk[2][3 * b + 1] = fma(T2, bz, blk[2][3 * b + 1]);
-                            blk[0][3 * b + 2] = fma(T0, by, blk[0][3 * b + 2]); blk[1][3 * b + 2] = fma(T1, by, blk[1][3 * b + 2]); blk[2][3 * b + 2] = fma(T2, by, blk[2][3 * b + 2]);
-                        }
+                        for (int q = 0; q < 12; ++q) cp_async8(dst + q * 128, src + (int64_t)q * er.ne_ext);
                     }
+                    cp_async_commit();
+                    asm volatile("cp.async.wait_group 0;" ::: "memory");
+                    __syncthreads();                                     // the three thirds of every element are in
+                    if (exists) {
+                        if (d == 0) integrate_gp<true, 0, -1>(gp, a, stage, 128, blk);     // warp-uniform
+                        else if (d == 1) integrate_gp<true, 1, -1>(gp, a, stage, 128, blk);
+                        else integrate_gp<true, 2, -1>(gp, a, stage, 128, blk);
+                    }
+                    __syncthreads();                                     // the buffer may be refilled
                 }
+            } else if (exists) {
+                if (d == 0) integrate_uniform<0>(a, blk);                                   // warp-uniform
+                else if (d == 1) integrate_uniform<1>(a, blk);
+                else integrate_uniform<2>(a, blk);
             }
-        }
-        __syncthreads();
-        // 8 rounds: in round b every warp adds block column b; for a fixed b the 8 warps
-        // (different a) target 8 different slots, so no two threads touch the same entry
+            // 8 rounds: in round b every warp adds its row of block column b; for a fixed b the 12 warps
+            // (different (a, d)) target 12 different (slot, row) pairs, so no two threads touch the same entry
 #pragma unroll
-        for (int b = 0; b < 8; ++b) {
-            if (exists) {
-                const int slot = (node_pz(b) - apz + 1) * 9 + (node_py(b) - apy + 1) * 3 + (node_px(b) - apx + 1);
-#pragma unroll
-                for (int d = 0; d < 3; ++d)
+            for (int b = 0; b < 8; ++b) {
+                if (exists) {
+                    const int kk0 = ((node_pz(b) - apz + 1) * 9 + (node_py(b) - apy + 1) * 3 + (node_px(b) - apx + 1)) * 9 + 3 * d;
 #pragma unroll
                     for (int cc = 0; cc < 3; ++cc) {
-                        const int kk = slot * 9 + 3 * d + cc;
-                        double *cell = tileA + ((kk >> 1) * TILE_NODES + lane) * 2 + (kk & 1);
-                        *cell = fma(blk[d][3 * b + cc], wg, *cell);
+                        double *cell = tileA + (kk0 + cc) * TILE_NODES + lane;
+                        *cell = fma(blk[3 * b + cc], wg, *cell);
                     }
+                }
+                __syncthreads();
             }
-            __syncthreads();
         }
-        // MatZeroRowsColumns (bcs.c:341-347) + PCJACOBI diagonal + coalesced store; warp a takes the
-        // entry pairs a, a+8, ...: the entry decoding (slot, row, col) is a warp-uniform table lookup
+        // PCJACOBI: the inverse diagonal (after MatZeroRowsColumns a Dirichlet row's diagonal is 1)
+        if (warp < 3 && valid && (!SYM || kl >= 0)) {
+            double v = tileA[(13 * 9 + 4 * warp) * TILE_NODES + lane];
+            if ((nbmask[13 * 32 + lane] >> warp) & 1u) v = 1.;
+            dinv[warp * g.S + g.G + ln0 + lane] = v != 0. ? 1. / v : 1.;
+        }
+        // MatZeroRowsColumns (bcs.c:341-347) + coalesced store; warp w takes the entry pairs w, w+12, ...
         const unsigned own = nbmask[13 * 32 + lane];
         auto apply_mask = [&](unsigned info, double v) -> double {
             if (info & 0x8000u) return 0.;
             const int slot = info & 31, rr = (info >> 5) & 3, cc = (info >> 7) & 3;
             const unsigned nb = nbmask[slot * 32 + lane];
-            const bool isdiag = (info >> 9) & 1u;
-            if (((own >> rr) & 1u) || ((nb >> cc) & 1u)) v = isdiag ? 1. : 0.;
-            if (SYM && kl < 0 && slot < 18) v = 0.;                  // ghost plane: only the blocks towards the slab
-            if (isdiag && valid && (!SYM || kl >= 0)) dinv[rr * g.S + g.G + ln0 + lane] = v != 0. ? 1. / v : 1.;
+            if (((own >> rr) & 1u) || ((nb >> cc) & 1u)) v = ((info >> 9) & 1u) ? 1. : 0.;
             return v;
         };
-        // streaming stores: the operator must not push the tangents of the next plane out of L2
+        const bool ghost_plane = SYM && kl < 0;                           // only the blocks towards the slab (slots 18..26) survive
         if (SYM) {
             double2 *At = A + tile * (SYM_PAIRS * TILE_NODES) + lane;
-            for (int pr = a; pr < SYM_PAIRS; pr += 8) {
-                const int kk0 = 117 + 2 * pr;                          // odd: the pair straddles two pairs of the staging tile
-                const double v0 = apply_mask(c_kkinfo.v[kk0], tileA[((kk0 >> 1) * TILE_NODES + lane) * 2 + 1]);
-                const double v1 = apply_mask(c_kkinfo.v[kk0 + 1], tileA[(((kk0 + 1) >> 1) * TILE_NODES + lane) * 2]);
-                __stcs(At + pr * TILE_NODES, make_double2(v0, v1));
+            for (int pr = warp; pr < SYM_PAIRS; pr += ASM_WARPS) {
+                const int kk0 = 117 + 2 * pr;
+                double v0 = tileA[kk0 * TILE_NODES + lane], v1 = tileA[(kk0 + 1) * TILE_NODES + lane];
+                if (masked_tile) { v0 = apply_mask(c_kkinfo.v[kk0], v0); v1 = apply_mask(c_kkinfo.v[kk0 + 1], v1); }
+                if (ghost_plane) { if (kk0 < 18 * 9) v0 = 0.; if (kk0 + 1 < 18 * 9) v1 = 0.; }
+                if (stream_stores) __stcs(At + pr * TILE_NODES, make_double2(v0, v1));
+                else At[pr * TILE_NODES] = make_double2(v0, v1);
             }
         } else {
             double2 *At = A + tile * (PAIRS * TILE_NODES) + lane;
             const unsigned *info2 = reinterpret_cast<const unsigned *>(c_kkinfo.v);      // two 16-bit entries per pair
-            for (int pr = a; pr < PAIRS; pr += 8) {
-                const unsigned info = info2[pr];
-                const double2 t2 = *reinterpret_cast<const double2 *>(tileA + (pr * TILE_NODES + lane) * 2);
-                __stcs(At + pr * TILE_NODES, make_double2(apply_mask(info & 0xffffu, t2.x), apply_mask(info >> 16, t2.y)));
+            for (int pr = warp; pr < PAIRS; pr += ASM_WARPS) {
+                double2 o2 = make_double2(tileA[(2 * pr) * TILE_NODES + lane], tileA[(2 * pr + 1) * TILE_NODES + lane]);
+                if (masked_tile) {
+                    const unsigned info = info2[pr];
+                    o2 = make_double2(apply_mask(info & 0xffffu, o2.x), apply_mask(info >> 16, o2.y));
+                }
+                if (stream_stores) __stcs(At + pr * TILE_NODES, o2);
+                else At[pr * TILE_NODES] = o2;
             }
         }
         __syncthreads();

@@ -980,16 +980,21 @@ template <bool SYM>
 static int launch_assemble_elements(macroc_ctx *c, bool per_gp, double2 *A, int64_t tile_lo, int64_t tile_hi)
 {
     const int64_t tpp = SYM ? sym_tiles_per_plane(c->g, c->sg) : std::max<int64_t>(1, (c->g.npl + TILE_NODES - 1) / TILE_NODES);
-    const int smem = TILE_DOUBLES * (int)sizeof(double) + 27 * 32;
+    static const int knob_cb = getenv("MACROC_ASM_COLBLOCK") ? atoi(getenv("MACROC_ASM_COLBLOCK")) : 64;   // <= 0: linear order
+    static const int knob_st = getenv("MACROC_ASM_STREAM") ? atoi(getenv("MACROC_ASM_STREAM")) : 1;
+    const int64_t colblock = knob_cb > 0 ? std::min<int64_t>(knob_cb, tpp) : tpp;
+    const int smem = per_gp ? ASM_SMEM_PER_GP : ASM_SMEM_UNIFORM;     // per-GP: + two staging buffers for the tangents
     static bool configured[64] = {false};                     // function attributes are per device
     if (!configured[c->device & 63]) {
-        CU(c, cudaFuncSetAttribute(k_assemble_elements<true, SYM>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        CU(c, cudaFuncSetAttribute(k_assemble_elements<false, SYM>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CU(c, cudaFuncSetAttribute(k_assemble_elements<true, SYM>, cudaFuncAttributeMaxDynamicSharedMemorySize, ASM_SMEM_PER_GP));
+        CU(c, cudaFuncSetAttribute(k_assemble_elements<false, SYM>, cudaFuncAttributeMaxDynamicSharedMemorySize, ASM_SMEM_UNIFORM));
         configured[c->device & 63] = true;
     }
-    const int blocks = (int)std::min<int64_t>(tile_hi - tile_lo, 148 * 3);
-    if (per_gp) k_assemble_elements<true, SYM><<<blocks, 256, smem, c->stream>>>(c->g, c->sg, c->er, c->geo.wg, c->ctan, c->nodemask, A, c->vec[V_DINV], tile_lo, tile_hi, tpp);
-    else k_assemble_elements<false, SYM><<<blocks, 256, smem, c->stream>>>(c->g, c->sg, c->er, c->geo.wg, c->ctan, c->nodemask, A, c->vec[V_DINV], tile_lo, tile_hi, tpp);
+    // exactly the resident CTAs (2 per SM): with more, the waves would run one after the other and the
+    // traversal's locality (neighbouring rows and planes in flight together, their tangents shared in L2) is lost
+    const int blocks = (int)std::min<int64_t>(tile_hi - tile_lo, 148 * 2);
+    if (per_gp) k_assemble_elements<true, SYM><<<blocks, ASM_THREADS, smem, c->stream>>>(c->g, c->sg, c->er, c->geo.wg, c->ctan, c->nodemask, A, c->vec[V_DINV], tile_lo, tile_hi, tpp, colblock, knob_st);
+    else k_assemble_elements<false, SYM><<<blocks, ASM_THREADS, smem, c->stream>>>(c->g, c->sg, c->er, c->geo.wg, c->ctan, c->nodemask, A, c->vec[V_DINV], tile_lo, tile_hi, tpp, colblock, knob_st);
     c->launches++;
     return MACROC_OK;
 }
@@ -1764,17 +1769,22 @@ extern "C" int macroc_fp64_probe(macroc_ctx *c, double *tflops)
     if (!c || !tflops) return MACROC_ERR_ARG;
     CU(c, cudaSetDevice(c->device));
     const int blocks = 148 * 8;                      // 8 CTAs of 256 threads per SM: every scheduler has 16 warps to pick from
+    BIND_CONSTANTS(c);
     double best = 0.;
-    for (int r = 0; r < 6; ++r) {
-        CU(c, cudaEventRecord(c->ev_t0, c->stream));
-        LAUNCH(c, k_fp64_probe, blocks, 256, c->sums, 1.0 + r);
-        CU(c, cudaEventRecord(c->ev_t1, c->stream));
-        CU(c, cudaEventSynchronize(c->ev_t1));
-        float ms = 0.f;
-        CU(c, cudaEventElapsedTime(&ms, c->ev_t0, c->ev_t1));
-        const double flops = 2.0 * FP64_PROBE_CHAINS * (double)FP64_PROBE_ITERS * 256.0 * blocks;
-        if (r >= 1 && ms > 0.f) best = std::max(best, flops / (ms * 1e-3) / 1e12);   // first launch: warm-up
-    }
+    // two operand forms: three register operands (register-port bound, ~33 TFLOP/s) and a constant-bank
+    // multiplier (the form of the unrolled element kernel; ~37 TFLOP/s): the better one is the pipe's rate
+    for (int mode = 0; mode < 2; ++mode)
+        for (int r = 0; r < 6; ++r) {
+            CU(c, cudaEventRecord(c->ev_t0, c->stream));
+            if (mode) LAUNCH(c, k_fp64_probe_const, blocks, 256, c->sums, 1.0 + r);
+            else LAUNCH(c, k_fp64_probe, blocks, 256, c->sums, 1.0 + r);
+            CU(c, cudaEventRecord(c->ev_t1, c->stream));
+            CU(c, cudaEventSynchronize(c->ev_t1));
+            float ms = 0.f;
+            CU(c, cudaEventElapsedTime(&ms, c->ev_t0, c->ev_t1));
+            const double flops = 2.0 * FP64_PROBE_CHAINS * (double)FP64_PROBE_ITERS * 256.0 * blocks;
+            if (r >= 1 && ms > 0.f) best = std::max(best, flops / (ms * 1e-3) / 1e12);   // first launch: warm-up
+        }
     CU(c, cudaGetLastError());
     *tflops = best;
     return MACROC_OK;

@@ -945,4 +945,22 @@ k_fp64_probe(double *out, double seed)
     if (s == 12345.678) out[0] = s;            // never true: keeps the chains alive
 }
 
+// the same probe with the multiplier taken from the constant bank (the form the unrolled element kernel uses)
+__global__ void __launch_bounds__(256)
+k_fp64_probe_const(double *out, double seed)
+{
+    double acc[FP64_PROBE_CHAINS];
+    const double b = 1e-9 * (threadIdx.x + 1);
+#pragma unroll
+    for (int q = 0; q < FP64_PROBE_CHAINS; ++q) acc[q] = seed + q;
+    for (int it = 0; it < FP64_PROBE_ITERS; ++it) {
+#pragma unroll
+        for (int q = 0; q < FP64_PROBE_CHAINS; ++q) acc[q] = fma(acc[q], c_dsh[q & 7][(q >> 1) & 7][q % 3], b);
+    }
+    double s = 0.;
+#pragma unroll
+    for (int q = 0; q < FP64_PROBE_CHAINS; ++q) s += acc[q];
+    if (s == 12345.678) out[0] = s;
+}
+
 }  // namespace macroc
