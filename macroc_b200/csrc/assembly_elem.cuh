@@ -163,11 +163,11 @@ __constant__ KkInfo c_kkinfo = make_kkinfo();
 // The Gauss-point loop is fully unrolled so that every shape-function derivative of the block
 // columns is an immediate constant-bank operand of its DFMA; wg is applied once, when a thread adds
 // its 3 x 24 row block to the tile.
-constexpr int ASM_WARPS = 12;                                             // 4 local nodes (x 2 passes) x 3 block rows
+constexpr int ASM_WARPS = 24;                                             // 8 local nodes x 3 block rows
 constexpr int ASM_THREADS = ASM_WARPS * 32;
 constexpr int ASM_STAGE_OFFSET = TILE_DOUBLES * 8 + 27 * 32 + 32;          // 16-byte aligned, behind the tile and the masks
 constexpr int ASM_SMEM_UNIFORM = TILE_DOUBLES * 8 + 27 * 32;
-constexpr int ASM_SMEM_PER_GP = ASM_STAGE_OFFSET + 36 * 128 * 8;           // + one staging buffer [36][4 nodes ah][32 lanes]: 2 CTAs fit an SM
+constexpr int ASM_SMEM_PER_GP = ASM_STAGE_OFFSET + 2 * 36 * 256 * 8;       // + two staging buffers [36][8 nodes a][32 lanes]
 
 // Row D of the 3 x 24 row block (B_a^T C B) of one element, one Gauss point:
 //   T[k]      = sum_r B_a[r][D] C[r][k]            -- B_a's column D has three non-zeros
@@ -213,19 +213,25 @@ __device__ __forceinline__ void integrate_uniform(int a, double (&blk)[24])
     integrate_gp<false, D, 6>(6, a, nullptr, 0, blk); integrate_gp<false, D, 7>(7, a, nullptr, 0, blk);
 }
 
-// General Jacobian assembly (assembly.c:85-108 with a tangent per Gauss point).  One CTA of 12 warps per
-// operator tile, two CTAs per SM: warp (ah, d), lane = node; in pass p the thread integrates row d of the
-// 3 x 24 row block of the element in which its node is local node a = ah + 4 p (24 accumulators, 720 FMA),
-// then the 12 warps add their rows into the tile in shared memory in 8 conflict-free rounds (round b: block
-// column b; distinct (a, d) hit distinct entries).  After both passes the Dirichlet mask is applied -- tiles
-// with no Dirichlet dof in reach, the vast majority, skip it -- and the tile leaves as one contiguous store.
-// The second CTA of the SM integrates while this one reduces and stores.  Per-Gauss-point tangents are
-// staged through shared memory per Gauss point (cp.async; the three row threads of a node share one copy).
+// General Jacobian assembly (assembly.c:85-108 with a tangent per Gauss point), one CTA of 24 warps per
+// operator tile: warp (a, d) = local node a of the element x row d of its 3 x 24 row block, lane = node.
+// Thread (a, d, lane) integrates row d of the block of the element in which its node is local node a
+// (24 accumulators, 720 FMA), the 24 warps add their rows into the tile in shared memory in 8
+// conflict-free rounds (round b: block column b; distinct (a, d) hit distinct entries), the Dirichlet
+// mask is applied -- tiles with no Dirichlet dof in reach, the vast majority, skip it -- and the tile
+// leaves as one contiguous store.  Per-Gauss-point tangents are staged through shared memory one Gauss
+// point ahead (cp.async; the three row threads of a node share one copy, two barriers per Gauss point):
+// 8 memory round trips per tile, all of them overlapped, instead of 48 exposed ones.
 // SYM: the tile is a row tile of the symmetric layout (spmv_sym.cuh) and only the slots 13..26 are
 // stored -- the tangent must then be symmetric (Ke is; the reference never relies on it, MATAIJ stores
 // both halves).  wg is applied once, when a thread adds its row to the tile.
+// Measured and rejected (256^3, uniform / per-GP tangents): 8 warps x 72 accumulators (42 / 63 ms; 2 warps
+// per scheduler cannot keep the FP64 pipe busy), this kernel with the 24 warps split into two co-resident
+// 12-warp CTAs that take two local nodes each (33.8 / 72.7 ms: no better, 3 integrating warps per
+// scheduler do not saturate the pipe either), grids larger than the resident CTAs (the traversal's locality
+// is lost: 75 GB of tangent reads instead of ~40).
 template <bool PER_GP, bool SYM>
-__global__ void __launch_bounds__(ASM_THREADS, 2)
+__global__ void __launch_bounds__(ASM_THREADS, 1)
 k_assemble_elements(GridDev g, SymGeom sg, ElemRange er, double wg, const double *__restrict__ ctan_gp,
                     const uint8_t *__restrict__ nodemask, double2 *__restrict__ A, double *__restrict__ dinv,
                     int64_t tile_lo, int64_t tile_hi, int64_t tpp /* tiles per plane (rounded up for the full layout) */,
@@ -238,11 +244,16 @@ k_assemble_elements(GridDev g, SymGeom sg, ElemRange er, double wg, const double
     double *tileA = reinterpret_cast<double *>(smem_raw);                  // 244 x 32 doubles = TILE_DOUBLES
     uint8_t *nbmask = smem_raw + TILE_DOUBLES * sizeof(double);            // [27][32]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int ah = warp / 3, d = warp - 3 * ah;
+    const int a = warp / 3, d = warp - 3 * a;
+    const int apx = node_px(a), apy = node_py(a), apz = node_pz(a);
     const int64_t per_layer = er.nex * er.ney;
-    // staging of the tangents (PER_GP): [36 entries][ah][lane]; thread (ah, d, lane) copies the entries
-    // 12 d .. 12 d + 11 of its element and reads the 18 its row needs after the barrier
-    double *stage = reinterpret_cast<double *>(smem_raw + ASM_STAGE_OFFSET) + ah * 32 + lane;
+    // staging of the tangents (PER_GP): [2 buffers][36 entries][a][lane]; thread (a, d, lane) copies the
+    // entries 12 d .. 12 d + 11 of its element and reads the 18 its row needs after the barrier
+    double *stage = reinterpret_cast<double *>(smem_raw + ASM_STAGE_OFFSET) + a * 32 + lane;
+    // where this thread's three cells of block column b live in the tile: entry kk = slot(a -> b) * 9 + 3 d + c
+    int cell0[8];
+#pragma unroll
+    for (int b = 0; b < 8; ++b) cell0[b] = ((node_pz(b) - apz + 1) * 9 + (node_py(b) - apy + 1) * 3 + (node_px(b) - apx + 1)) * 9 + 3 * d;
 
     // Traversal: column blocks of `colblock` tiles of a plane, swept through all planes before the next
     // block (an element's tangents are needed by the tiles of two rows and two planes: the second plane
@@ -279,6 +290,21 @@ k_assemble_elements(GridDev g, SymGeom sg, ElemRange er, double wg, const double
         }
         const bool valid = lane < nvalid;
         const int k = kl + g.zs;
+        // the element in which this node is local node a (it must be one whose tangents this rank holds)
+        const int ei = i - apx, ej = j - apy, ek = k - apz;
+        const bool exists = valid && ei >= 0 && ei < g.NX - 1 && ej >= 0 && ej < g.NY - 1 && ek >= 0 && ek < g.NZ - 1 &&
+                            ek >= er.ezs && ek < er.ezs + er.nez_ext;
+        const double *cg = (PER_GP && exists) ? ctan_gp + ((int64_t)(ek - er.ezs) * per_layer + ei + er.nex * (int64_t)ej) : nullptr;
+        auto stage_gp = [&](int gp) {               // this thread's third of the element's 36 entries of Gauss point gp
+            if (exists) {
+                double *dst = stage + (gp & 1) * (36 * 256) + (12 * d) * 256;
+                const double *src = cg + (int64_t)(gp * 36 + 12 * d) * er.ne_ext;
+#pragma unroll
+                for (int q = 0; q < 12; ++q) cp_async8(dst + q * 256, src + (int64_t)q * er.ne_ext);
+            }
+            cp_async_commit();
+        };
+        if (PER_GP) stage_gp(0);
         {
             double2 *z2 = reinterpret_cast<double2 *>(tileA);
             for (int q = threadIdx.x; q < TILE_DOUBLES / 2; q += blockDim.x) z2[q] = make_double2(0., 0.);
@@ -293,58 +319,42 @@ k_assemble_elements(GridDev g, SymGeom sg, ElemRange er, double wg, const double
             nbmask[q] = mk;
             anymask |= mk;
         }
+        double blk[24];
+#pragma unroll
+        for (int q = 0; q < 24; ++q) blk[q] = 0.;
+        if (PER_GP) {
+#pragma unroll 1
+            for (int gp = 0; gp < 8; ++gp) {
+                if (gp < 7) { stage_gp(gp + 1); asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+                else asm volatile("cp.async.wait_group 0;" ::: "memory");
+                __syncthreads();                                         // the three thirds of every element are in
+                const double *ck = stage + (gp & 1) * (36 * 256);
+                if (exists) {
+                    if (d == 0) integrate_gp<true, 0, -1>(gp, a, ck, 256, blk);          // warp-uniform
+                    else if (d == 1) integrate_gp<true, 1, -1>(gp, a, ck, 256, blk);
+                    else integrate_gp<true, 2, -1>(gp, a, ck, 256, blk);
+                }
+                __syncthreads();                                         // buffer (gp & 1) may be refilled two trips later
+            }
+        } else if (exists) {
+            if (d == 0) integrate_uniform<0>(a, blk);                                    // warp-uniform
+            else if (d == 1) integrate_uniform<1>(a, blk);
+            else integrate_uniform<2>(a, blk);
+        }
         // does any node of the tile, or any of its neighbours, carry a Dirichlet dof?  (block-uniform)
         const int masked_tile = __syncthreads_or(anymask != 0);          // also: the tile is zeroed, the masks are in
-#pragma unroll 1
-        for (int pass = 0; pass < 2; ++pass) {
-            const int a = ah + 4 * pass;
-            const int apx = node_px(a), apy = node_py(a), apz = node_pz(a);
-            // the element in which this node is local node a (it must be one whose tangents this rank holds)
-            const int ei = i - apx, ej = j - apy, ek = k - apz;
-            const bool exists = valid && ei >= 0 && ei < g.NX - 1 && ej >= 0 && ej < g.NY - 1 && ek >= 0 && ek < g.NZ - 1 &&
-                                ek >= er.ezs && ek < er.ezs + er.nez_ext;
-            double blk[24];
+        // 8 rounds: in round b every warp adds its row of block column b; for a fixed b the 24 warps
+        // (different (a, d)) target 24 different (slot, row) pairs, so no two threads touch the same entry
 #pragma unroll
-            for (int q = 0; q < 24; ++q) blk[q] = 0.;
-            if (PER_GP) {
-                const double *cg = exists ? ctan_gp + ((int64_t)(ek - er.ezs) * per_layer + ei + er.nex * (int64_t)ej) : nullptr;
-#pragma unroll 1
-                for (int gp = 0; gp < 8; ++gp) {
-                    if (exists) {                                        // this thread's third of the 36 entries
-                        double *dst = stage + (12 * d) * 128;
-                        const double *src = cg + (int64_t)(gp * 36 + 12 * d) * er.ne_ext;
+        for (int b = 0; b < 8; ++b) {
+            if (exists) {
 #pragma unroll
-                        for (int q = 0; q < 12; ++q) cp_async8(dst + q * 128, src + (int64_t)q * er.ne_ext);
-                    }
-                    cp_async_commit();
-                    asm volatile("cp.async.wait_group 0;" ::: "memory");
-                    __syncthreads();                                     // the three thirds of every element are in
-                    if (exists) {
-                        if (d == 0) integrate_gp<true, 0, -1>(gp, a, stage, 128, blk);     // warp-uniform
-                        else if (d == 1) integrate_gp<true, 1, -1>(gp, a, stage, 128, blk);
-                        else integrate_gp<true, 2, -1>(gp, a, stage, 128, blk);
-                    }
-                    __syncthreads();                                     // the buffer may be refilled
+                for (int cc = 0; cc < 3; ++cc) {
+                    double *cell = tileA + (cell0[b] + cc) * TILE_NODES + lane;
+                    *cell = fma(blk[3 * b + cc], wg, *cell);
                 }
-            } else if (exists) {
-                if (d == 0) integrate_uniform<0>(a, blk);                                   // warp-uniform
-                else if (d == 1) integrate_uniform<1>(a, blk);
-                else integrate_uniform<2>(a, blk);
             }
-            // 8 rounds: in round b every warp adds its row of block column b; for a fixed b the 12 warps
-            // (different (a, d)) target 12 different (slot, row) pairs, so no two threads touch the same entry
-#pragma unroll
-            for (int b = 0; b < 8; ++b) {
-                if (exists) {
-                    const int kk0 = ((node_pz(b) - apz + 1) * 9 + (node_py(b) - apy + 1) * 3 + (node_px(b) - apx + 1)) * 9 + 3 * d;
-#pragma unroll
-                    for (int cc = 0; cc < 3; ++cc) {
-                        double *cell = tileA + (kk0 + cc) * TILE_NODES + lane;
-                        *cell = fma(blk[3 * b + cc], wg, *cell);
-                    }
-                }
-                __syncthreads();
-            }
+            __syncthreads();
         }
         // PCJACOBI: the inverse diagonal (after MatZeroRowsColumns a Dirichlet row's diagonal is 1)
         if (warp < 3 && valid && (!SYM || kl >= 0)) {
@@ -352,7 +362,7 @@ k_assemble_elements(GridDev g, SymGeom sg, ElemRange er, double wg, const double
             if ((nbmask[13 * 32 + lane] >> warp) & 1u) v = 1.;
             dinv[warp * g.S + g.G + ln0 + lane] = v != 0. ? 1. / v : 1.;
         }
-        // MatZeroRowsColumns (bcs.c:341-347) + coalesced store; warp w takes the entry pairs w, w+12, ...
+        // MatZeroRowsColumns (bcs.c:341-347) + coalesced store; warp w takes the entry pairs w, w+24, ...
         const unsigned own = nbmask[13 * 32 + lane];
         auto apply_mask = [&](unsigned info, double v) -> double {
             if (info & 0x8000u) return 0.;

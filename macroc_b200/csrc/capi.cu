@@ -990,9 +990,9 @@ static int launch_assemble_elements(macroc_ctx *c, bool per_gp, double2 *A, int6
         CU(c, cudaFuncSetAttribute(k_assemble_elements<false, SYM>, cudaFuncAttributeMaxDynamicSharedMemorySize, ASM_SMEM_UNIFORM));
         configured[c->device & 63] = true;
     }
-    // exactly the resident CTAs (2 per SM): with more, the waves would run one after the other and the
+    // exactly the resident CTAs (1 per SM): with more, the waves would run one after the other and the
     // traversal's locality (neighbouring rows and planes in flight together, their tangents shared in L2) is lost
-    const int blocks = (int)std::min<int64_t>(tile_hi - tile_lo, 148 * 2);
+    const int blocks = (int)std::min<int64_t>(tile_hi - tile_lo, 148);
     if (per_gp) k_assemble_elements<true, SYM><<<blocks, ASM_THREADS, smem, c->stream>>>(c->g, c->sg, c->er, c->geo.wg, c->ctan, c->nodemask, A, c->vec[V_DINV], tile_lo, tile_hi, tpp, colblock, knob_st);
     else k_assemble_elements<false, SYM><<<blocks, ASM_THREADS, smem, c->stream>>>(c->g, c->sg, c->er, c->geo.wg, c->ctan, c->nodemask, A, c->vec[V_DINV], tile_lo, tile_hi, tpp, colblock, knob_st);
     c->launches++;
