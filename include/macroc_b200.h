@@ -211,6 +211,16 @@ int macroc_time_kernel(macroc_ctx *ctx, int what, int reps, int flush_l2, double
  * TFLOP/s: the denominator of the FP64-pipe fractions quoted for the matrix-free apply and the
  * element assembly (no FP64 figure is in MEASURED_PEAKS.json). */
 int macroc_fp64_probe(macroc_ctx *ctx, double *tflops);
+/* Measured rate of the fp64 tensor-core instruction (mma.sync.m8n8k4.f64, SASS DMMA.8x8x4), 8 independent
+ * accumulator tiles per warp, in TFLOP/s (512 flop per instruction). */
+int macroc_dmma_probe(macroc_ctx *ctx, double *tflops);
+/* A/B of the element contraction Ke = sum_gp B^T C_gp B wg (src/assembly.c:94-99) over all stored elements,
+ * tangents from the per-Gauss-point arrays (needs MACROC_MAT_PER_GP + macroc_homogenize): variant 0 = the
+ * sparsity-aware DFMA form the product kernels use, 1 = dense mma.m8n8k4.f64 tiles (24 DMMA per Gauss point),
+ * 2 = the same with the upper tiles only (18 DMMA).  Mean milliseconds of `reps` launches after one warm-up;
+ * the matrices of the first n_full elements are copied to full_host[n_full][24][24] (row-major).
+ * A measurement hook (north_star: "DMMA ... only if ncu shows a win over FFMA"), not part of the solve path. */
+int macroc_contraction_ab(macroc_ctx *ctx, int variant, int reps, int n_full, double *full_host, double *ms_mean);
 /* how the CG dot products are reduced over the ranks: 0 one rank, 1 ncclAllReduce, 2 peer-mapped
  * mailboxes inside the reduction kernels (csrc/cg_mbox.cuh), 3 loopback host sum */
 int macroc_allreduce_path(const macroc_ctx *ctx);

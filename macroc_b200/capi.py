@@ -37,7 +37,7 @@ EXPORTS = [
     "macroc_time_kernel", "macroc_launch_count", "macroc_device_synchronize", "macroc_version",
     "macroc_event_record", "macroc_event_elapsed_ms", "macroc_profile_enable", "macroc_profile_get",
     "macroc_homogenize", "macroc_gp_arrays", "macroc_set_gp_data", "macroc_set_operator", "macroc_write_pvtu",
-    "macroc_loopback_id", "macroc_fp64_probe", "macroc_profile_get_solve", "macroc_allreduce_path",
+    "macroc_loopback_id", "macroc_fp64_probe", "macroc_dmma_probe", "macroc_contraction_ab", "macroc_profile_get_solve", "macroc_allreduce_path",
 ]
 
 
@@ -132,6 +132,8 @@ def lib():
     L.macroc_get_strain_stress.argtypes = [vp, C.c_void_p, C.c_void_p, C.POINTER(C.c_int64)]
     L.macroc_time_kernel.argtypes = [vp, C.c_int, C.c_int, C.c_int, dp]
     L.macroc_fp64_probe.argtypes = [vp, dp]
+    L.macroc_dmma_probe.argtypes = [vp, dp]
+    L.macroc_contraction_ab.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_void_p, dp]
     L.macroc_allreduce_path.argtypes = [vp]
     L.macroc_launch_count.argtypes = [vp]; L.macroc_launch_count.restype = C.c_uint64
     L.macroc_device_synchronize.argtypes = [vp]
@@ -411,6 +413,19 @@ class MacroC:
         t = C.c_double()
         self._chk(self._L.macroc_fp64_probe(self._h, C.byref(t)))
         return t.value
+
+    def dmma_probe(self) -> float:
+        """Measured rate of mma.sync.m8n8k4.f64 (DMMA) in TFLOP/s."""
+        t = C.c_double()
+        self._chk(self._L.macroc_dmma_probe(self._h, C.byref(t)))
+        return t.value
+
+    def contraction_ab(self, variant: int, reps: int = 3, n_full: int = 0):
+        """(ms, Ke[n_full][24][24]) of the element-contraction A/B kernels: 0 DFMA, 1 DMMA dense, 2 DMMA upper tiles."""
+        ms = C.c_double()
+        full = np.zeros((max(n_full, 1), 24, 24))
+        self._chk(self._L.macroc_contraction_ab(self._h, variant, reps, n_full, full.ctypes.data if n_full else None, C.byref(ms)))
+        return ms.value, full[:n_full]
 
     def event_record(self, slot: int):
         self._chk(self._L.macroc_event_record(self._h, slot))

@@ -25,6 +25,8 @@
 #include "kernels.cuh"
 #include "spmv_tma.cuh"
 #include "assembly_elem.cuh"
+#include "assembly_node.cuh"
+#include "dmma_ab.cuh"
 #include "spmv_sym.cuh"
 #include "loopback.h"
 #include "cg_mbox.cuh"
@@ -57,10 +59,11 @@ struct macroc_ctx {
     double2 *Asym = nullptr;         // symmetric storage (14 of 27 slots), MACROC_OP_ASSEMBLED_SYM; points at tile 0
     double2 *Asym_alloc = nullptr;   // start of the allocation: the ghost plane below (if any), then the slab
     SymGeom sg = {1, 0};
+    int asm_variant = 0, asm_colblock = 64, asm_ctas_per_sm = 2;   // element-Jacobian knobs (MACROC_ASM_*)
     int sym_R = 0, sym_nseg = 0, sym_variant = 0, sym_hint = 0;   // tuning overrides (MACROC_SYM_R / _NSEG / _VARIANT / _HINT, read once at create)
     bool A_valid = false, mf_ready = false, Asym_valid = false;
     double *Ke = nullptr, *T = nullptr;
-    uint8_t *nodemask = nullptr, *ghostflag = nullptr;
+    uint8_t *nodemask = nullptr, *masksum = nullptr, *ghostflag = nullptr;   // masksum[q] = OR of nodemask[32 q .. 32 q + 31]
     double *xy_halo = nullptr;       // 4 send + 4 receive staging buffers of the x / y halo
     size_t xy_halo_stride = 0;
     double *consts = nullptr;        // device copy of {dsh[192], D[36], T[6561]} for bind_constants
@@ -362,7 +365,7 @@ static int ctx_free(macroc_ctx *c)
     }
     for (cudaGraphExec_t ge : c->cg_graph) if (ge) cudaGraphExecDestroy(ge);
     for (int i = 0; i < V_COUNT; ++i) cudaFree(c->vec[i]);
-    cudaFree(c->A); cudaFree(c->Asym_alloc); cudaFree(c->Ke); cudaFree(c->T); cudaFree(c->nodemask); cudaFree(c->bc_idx); cudaFree(c->bc_coef);
+    cudaFree(c->A); cudaFree(c->Asym_alloc); cudaFree(c->Ke); cudaFree(c->T); cudaFree(c->nodemask); cudaFree(c->masksum); cudaFree(c->bc_idx); cudaFree(c->bc_coef);
     cudaFree(c->partial); cudaFree(c->sums); cudaFree(c->sc); cudaFree(c->stage); cudaFree(c->strain); cudaFree(c->stress);
     cudaFree(c->ctan); cudaFree(c->scratch); cudaFree(c->consts); cudaFree(c->gp_halo); cudaFree(c->ghostflag); cudaFree(c->xy_halo);
     cudaFree(c->flush);
@@ -471,6 +474,9 @@ extern "C" int macroc_create(const macroc_config *cfg, int rank, int nranks, con
     if (const char *v = getenv("MACROC_SYM_NSEG")) c->sym_nseg = atoi(v);
     if (const char *v = getenv("MACROC_SYM_VARIANT")) c->sym_variant = atoi(v);
     if (const char *v = getenv("MACROC_SYM_HINT")) c->sym_hint = atoi(v);
+    if (const char *v = getenv("MACROC_ASM_VARIANT")) c->asm_variant = atoi(v);
+    if (const char *v = getenv("MACROC_ASM_COLBLOCK")) c->asm_colblock = atoi(v);
+    if (const char *v = getenv("MACROC_ASM_CTAS")) c->asm_ctas_per_sm = atoi(v);
     if (cfg->device >= 0) c->device = cfg->device;
     else if (cudaGetDevice(&c->device) != cudaSuccess) c->device = 0;
 #define CUC(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { g_last_error = std::string(#call) + " -> " + cudaGetErrorString(_e); ctx_free(c); return MACROC_ERR_CUDA; } } while (0)
@@ -552,6 +558,10 @@ extern "C" int macroc_create(const macroc_config *cfg, int rank, int nranks, con
         c->nbc = (int)own_idx.size();
         CUC(cudaMalloc(&c->nodemask, (size_t)g.S));
         CUC(cudaMemcpyAsync(c->nodemask, mask.data(), (size_t)g.S, cudaMemcpyHostToDevice, c->stream));
+        std::vector<uint8_t> msum((size_t)(g.S / 32 + 1), 0);
+        for (int64_t q = 0; q < g.S; ++q) msum[(size_t)(q >> 5)] |= mask[(size_t)q];
+        CUC(cudaMalloc(&c->masksum, msum.size()));
+        CUC(cudaMemcpy(c->masksum, msum.data(), msum.size(), cudaMemcpyHostToDevice));
         if (c->nbc) {
             CUC(cudaMalloc(&c->bc_idx, sizeof(int64_t) * c->nbc));
             CUC(cudaMalloc(&c->bc_coef, sizeof(double) * c->nbc));
@@ -980,21 +990,36 @@ template <bool SYM>
 static int launch_assemble_elements(macroc_ctx *c, bool per_gp, double2 *A, int64_t tile_lo, int64_t tile_hi)
 {
     const int64_t tpp = SYM ? sym_tiles_per_plane(c->g, c->sg) : std::max<int64_t>(1, (c->g.npl + TILE_NODES - 1) / TILE_NODES);
-    static const int knob_cb = getenv("MACROC_ASM_COLBLOCK") ? atoi(getenv("MACROC_ASM_COLBLOCK")) : 64;   // <= 0: linear order
-    static const int knob_st = getenv("MACROC_ASM_STREAM") ? atoi(getenv("MACROC_ASM_STREAM")) : 1;
-    const int64_t colblock = knob_cb > 0 ? std::min<int64_t>(knob_cb, tpp) : tpp;
-    const int smem = per_gp ? ASM_SMEM_PER_GP : ASM_SMEM_UNIFORM;     // per-GP: + two staging buffers for the tangents
-    static bool configured[64] = {false};                     // function attributes are per device
+    const int64_t colblock = c->asm_colblock > 0 ? std::min<int64_t>(c->asm_colblock, tpp) : tpp;
+    if (c->asm_variant == 1) {
+        // the element-centric kernel of round 2's first half (24 warps, shared-memory reduction rounds): kept for the A/B
+        const int smem = per_gp ? ASM_SMEM_PER_GP : ASM_SMEM_UNIFORM;     // per-GP: + two staging buffers for the tangents
+        static bool configured[64] = {false};                     // function attributes are per device
+        if (!configured[c->device & 63]) {
+            CU(c, cudaFuncSetAttribute(k_assemble_elements<true, SYM>, cudaFuncAttributeMaxDynamicSharedMemorySize, ASM_SMEM_PER_GP));
+            CU(c, cudaFuncSetAttribute(k_assemble_elements<false, SYM>, cudaFuncAttributeMaxDynamicSharedMemorySize, ASM_SMEM_UNIFORM));
+            configured[c->device & 63] = true;
+        }
+        const int blocks = (int)std::min<int64_t>(tile_hi - tile_lo, 148);
+        if (per_gp) k_assemble_elements<true, SYM><<<blocks, ASM_THREADS, smem, c->stream>>>(c->g, c->sg, c->er, c->geo.wg, c->ctan, c->nodemask, A, c->vec[V_DINV], tile_lo, tile_hi, tpp, colblock, 1);
+        else k_assemble_elements<false, SYM><<<blocks, ASM_THREADS, smem, c->stream>>>(c->g, c->sg, c->er, c->geo.wg, c->ctan, c->nodemask, A, c->vec[V_DINV], tile_lo, tile_hi, tpp, colblock, 1);
+        c->launches++;
+        return MACROC_OK;
+    }
+    // node-centric kernels (assembly_node.cuh)
+    static bool configured[64] = {false};
     if (!configured[c->device & 63]) {
-        CU(c, cudaFuncSetAttribute(k_assemble_elements<true, SYM>, cudaFuncAttributeMaxDynamicSharedMemorySize, ASM_SMEM_PER_GP));
-        CU(c, cudaFuncSetAttribute(k_assemble_elements<false, SYM>, cudaFuncAttributeMaxDynamicSharedMemorySize, ASM_SMEM_UNIFORM));
+        CU(c, cudaFuncSetAttribute(k_assemble_nodes_pergp<SYM>, cudaFuncAttributeMaxDynamicSharedMemorySize, ASMN_SMEM_PER_GP));
         configured[c->device & 63] = true;
     }
-    // exactly the resident CTAs (1 per SM): with more, the waves would run one after the other and the
-    // traversal's locality (neighbouring rows and planes in flight together, their tangents shared in L2) is lost
-    const int blocks = (int)std::min<int64_t>(tile_hi - tile_lo, 148);
-    if (per_gp) k_assemble_elements<true, SYM><<<blocks, ASM_THREADS, smem, c->stream>>>(c->g, c->sg, c->er, c->geo.wg, c->ctan, c->nodemask, A, c->vec[V_DINV], tile_lo, tile_hi, tpp, colblock, knob_st);
-    else k_assemble_elements<false, SYM><<<blocks, ASM_THREADS, smem, c->stream>>>(c->g, c->sg, c->er, c->geo.wg, c->ctan, c->nodemask, A, c->vec[V_DINV], tile_lo, tile_hi, tpp, colblock, knob_st);
+    if (per_gp) {
+        // exactly the resident CTAs, so that neighbouring rows and planes are in flight together and share their tangents in L2
+        const int blocks = (int)std::min<int64_t>(tile_hi - tile_lo, 148 * std::max(1, c->asm_ctas_per_sm));
+        k_assemble_nodes_pergp<SYM><<<blocks, ASMN_THREADS, ASMN_SMEM_PER_GP, c->stream>>>(c->g, c->sg, c->er, c->geo.wg, c->ctan, c->nodemask, c->masksum, A, c->vec[V_DINV], tile_lo, tile_hi, tpp, colblock);
+    } else {
+        const int blocks = (int)std::min<int64_t>(cdiv64((tile_hi - tile_lo) * 9, ASMU_WARPS), 148 * ASMU_CTAS_PER_SM);
+        k_assemble_nodes_uniform<SYM><<<blocks, ASMU_WARPS * 32, 0, c->stream>>>(c->g, c->sg, c->er, c->geo.wg, c->nodemask, c->masksum, A, c->vec[V_DINV], tile_lo, tile_hi, tpp);
+    }
     c->launches++;
     return MACROC_OK;
 }
@@ -1057,8 +1082,9 @@ static int spmv_launch_tma(macroc_ctx *c, double *p, double *w, int64_t first, i
     using SM = SpmvTmaSmem<WARPS, NSTAGE>;
     static bool configured[64] = {false};          // function attributes are per device
     if (!configured[c->device & 63]) {
-        cudaFuncSetAttribute(k_spmv_tma<WARPS, NSTAGE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::total);
-        cudaFuncSetAttribute(k_spmv_tma<WARPS, NSTAGE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::total);
+        cudaError_t e1 = cudaFuncSetAttribute(k_spmv_tma<WARPS, NSTAGE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::total);
+        cudaError_t e2 = cudaFuncSetAttribute(k_spmv_tma<WARPS, NSTAGE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::total);
+        if (e1 != cudaSuccess || e2 != cudaSuccess) return -1;
         configured[c->device & 63] = true;
     }
     int per_sm = std::max(1, (227 * 1024) / (SM::total + 1024));
@@ -1190,8 +1216,9 @@ static int apply_operator(macroc_ctx *c, int op, double *p, double *w, bool with
             const int64_t ntile = (int64_t)tiles_x * tiles_y * ((k1 - k0 + MF_TZ - 1) / MF_TZ);
             static bool configured[64] = {false};
             if (!configured[c->device & 63]) {
-                cudaFuncSetAttribute(k_apply_mf3d<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MF_SMEM);
-                cudaFuncSetAttribute(k_apply_mf3d<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MF_SMEM);
+                cudaError_t e1 = cudaFuncSetAttribute(k_apply_mf3d<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MF_SMEM);
+                cudaError_t e2 = cudaFuncSetAttribute(k_apply_mf3d<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MF_SMEM);
+                if (e1 != cudaSuccess || e2 != cudaSuccess) { rc_run = MACROC_ERR_CUDA; return; }
                 configured[c->device & 63] = true;
             }
             // an odd grid: the tile -> CTA map must not be periodic in the 8 x-tiles of a row, or the
@@ -1790,6 +1817,64 @@ extern "C" int macroc_fp64_probe(macroc_ctx *c, double *tflops)
     return MACROC_OK;
 }
 
+extern "C" int macroc_dmma_probe(macroc_ctx *c, double *tflops)
+{
+    if (!c || !tflops) return MACROC_ERR_ARG;
+    CU(c, cudaSetDevice(c->device));
+    const int blocks = 148 * 8;
+    double best = 0.;
+    for (int r = 0; r < 6; ++r) {
+        CU(c, cudaEventRecord(c->ev_t0, c->stream));
+        LAUNCH(c, k_dmma_probe, blocks, 256, c->sums, 1.0 + r);
+        CU(c, cudaEventRecord(c->ev_t1, c->stream));
+        CU(c, cudaEventSynchronize(c->ev_t1));
+        float ms = 0.f;
+        CU(c, cudaEventElapsedTime(&ms, c->ev_t0, c->ev_t1));
+        const double flops = 512.0 * DMMA_PROBE_CHAINS * (double)DMMA_PROBE_ITERS * 8.0 * blocks;   // 8 warps per CTA, 2 x 8 x 8 x 4 per DMMA
+        if (r >= 1 && ms > 0.f) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+    }
+    CU(c, cudaGetLastError());
+    *tflops = best;
+    return MACROC_OK;
+}
+
+extern "C" int macroc_contraction_ab(macroc_ctx *c, int variant, int reps, int n_full, double *full_host, double *ms_mean)
+{
+    if (!c || !ms_mean || reps <= 0 || variant < 0 || variant > 2 || n_full < 0 || (n_full > 0 && !full_host)) return MACROC_ERR_ARG;
+    if (!c->ctan) FAIL(c, MACROC_ERR_ARG, "contraction_ab: no Gauss-point tangents (material MACROC_MAT_PER_GP, call homogenize)");
+    CU(c, cudaSetDevice(c->device));
+    BIND_CONSTANTS(c);
+    const int64_t ne = c->er.ne_ext;
+    double *rowsum = nullptr, *full = nullptr;
+    CU(c, cudaMalloc(&rowsum, sizeof(double) * 24 * (size_t)ne));
+    if (cudaMalloc(&full, sizeof(double) * 576 * (size_t)std::max(1, n_full)) != cudaSuccess) { cudaFree(rowsum); FAIL(c, MACROC_ERR_MEM, "contraction_ab: out of memory"); }
+    cudaError_t ea = cudaSuccess;
+    if (variant == 0) ea = cudaFuncSetAttribute(k_ab_dfma, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM_DFMA);
+    else if (variant == 1) ea = cudaFuncSetAttribute(k_ab_dmma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM_DMMA);
+    else ea = cudaFuncSetAttribute(k_ab_dmma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM_DMMA);
+    int rc = MACROC_OK;
+    double total = 0.;
+    const int blocks = (int)std::min<int64_t>((ne + AB_ELEMS - 1) / AB_ELEMS, 148);
+    for (int r = 0; r < reps + 1 && ea == cudaSuccess; ++r) {              // the first launch is a warm-up
+        cudaEventRecord(c->ev_t0, c->stream);
+        if (variant == 0) k_ab_dfma<<<blocks, AB_DFMA_THREADS, AB_SMEM_DFMA, c->stream>>>(c->ctan, ne, ne, c->geo.wg, rowsum, full, n_full);
+        else if (variant == 1) k_ab_dmma<false><<<blocks, AB_DMMA_WARPS * 32, AB_SMEM_DMMA, c->stream>>>(c->ctan, ne, ne, c->geo.wg, rowsum, full, n_full);
+        else k_ab_dmma<true><<<blocks, AB_DMMA_WARPS * 32, AB_SMEM_DMMA, c->stream>>>(c->ctan, ne, ne, c->geo.wg, rowsum, full, n_full);
+        c->launches++;
+        cudaEventRecord(c->ev_t1, c->stream);
+        ea = cudaEventSynchronize(c->ev_t1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, c->ev_t0, c->ev_t1);
+        if (r >= 1) total += ms;
+    }
+    if (ea == cudaSuccess) ea = cudaGetLastError();
+    if (ea == cudaSuccess && n_full > 0) ea = cudaMemcpy(full_host, full, sizeof(double) * 576 * (size_t)n_full, cudaMemcpyDeviceToHost);
+    cudaFree(rowsum); cudaFree(full);
+    if (ea != cudaSuccess) FAIL(c, MACROC_ERR_CUDA, "contraction_ab: %s", cudaGetErrorString(ea));
+    *ms_mean = total / reps;
+    return rc;
+}
+
 extern "C" int macroc_time_kernel(macroc_ctx *c, int what, int reps, int flush_l2, double *ms_mean)
 {
     if (!c || !ms_mean || reps <= 0) return MACROC_ERR_ARG;
@@ -1834,9 +1919,9 @@ extern "C" int macroc_time_kernel(macroc_ctx *c, int what, int reps, int flush_l
                 if (!rc) LAUNCH(c, k_reduce, 1, 256, c->partial, nparts, c->sums);
                 break;
             }
-            case 7: {                                   // per-element Jacobian kernel (tangent source per cfg.material)
+            case 7: case 17: {                          // per-element Jacobian kernel (tangent source per cfg.material); 17: symmetric layout
                 int save_op = c->cfg.op, save_j = c->cfg.jac_mode;
-                c->cfg.op = MACROC_OP_ASSEMBLED; c->cfg.jac_mode = MACROC_JAC_ELEMENT;
+                c->cfg.op = what == 17 ? MACROC_OP_ASSEMBLED_SYM : MACROC_OP_ASSEMBLED; c->cfg.jac_mode = MACROC_JAC_ELEMENT;
                 rc = macroc_assembly_jac(c);
                 c->cfg.op = save_op; c->cfg.jac_mode = save_j;
                 break;

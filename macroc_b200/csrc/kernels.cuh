@@ -29,7 +29,7 @@ __constant__ int c_sgn[8][3] = {{-1, -1, -1}, {+1, -1, -1}, {+1, +1, -1}, {-1, +
                                 {-1, -1, +1}, {+1, -1, +1}, {+1, +1, +1}, {-1, +1, +1}};
 // dsh[gp][n][d]: shape-function derivatives of the unit-cube element
 // (assembly.c:198-232), filled once by k_init_dsh and then read-only.
-__constant__ double c_dsh[8][8][3];
+__constant__ __align__(16) double c_dsh[8][8][3];
 __constant__ double c_D[36];                 // homogenised tangent (row-major 6x6)
 // class stencils T[27 classes][27 slots][3][3] (see k_stencil_table); interior class = 13
 __constant__ double c_T[27 * 243];

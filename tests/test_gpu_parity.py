@@ -358,6 +358,29 @@ def test_heterogeneous_gauss_point_data(op, NX, NY, NZ):
     assert rel_err(m.matmult(x, op), A @ x) < 1e-13
 
 
+@pytest.mark.parametrize("variant", [0, 1, 2])
+def test_contraction_ab_kernels_match_oracle_element_matrix(variant):
+    """The DFMA and the DMMA (mma.m8n8k4.f64) form of Ke = sum_gp B^T C_gp B wg -- the A/B the north_star asks for
+    -- against the oracle's element routine (reference loop assembly.c:94-99) on heterogeneous SPD tangents."""
+    NX, NY, NZ = 9, 5, 4
+    rng = np.random.default_rng(17)
+    m = M.MacroC(M.Config(NX=NX, NY=NY, NZ=NZ, bc_type=M.BC_BENDING, material=M.MAT_PER_GP))
+    o = O.Oracle(O.Config(NX=NX, NY=NY, NZ=NZ, bc_type=M.BC_BENDING))
+    ne = (NX - 1) * (NY - 1) * (NZ - 1)
+    Q = rng.standard_normal((ne, 8, 6, 6))
+    ctan = 1e6 * (Q @ Q.transpose(0, 1, 3, 2) + 6 * np.eye(6))
+    m.set_strains(); m.set_gp_data(ctan=ctan)
+    ms, Ke = m.contraction_ab(variant, reps=1, n_full=ne)
+    assert ms > 0
+    for e in range(ne):
+        ref = O.elem_jac(ctan[e].reshape(8, 36), o.wg).reshape(24, 24)
+        got = Ke[e]
+        if variant == 2:                       # upper 8x8 tiles only (symmetric tangent)
+            keep = np.triu(np.ones((3, 3), bool)).repeat(8, 0).repeat(8, 1)
+            ref, got = ref * keep, got * keep
+        assert rel_err(got, ref) < TOL_MAT
+
+
 def test_two_live_contexts_do_not_share_element_constants():
     """__constant__ tables are per device: contexts with different material / element size must
     re-bind them when they interleave."""
