@@ -427,7 +427,8 @@ def run_gpu_arm(args):
         if op == M.OP_ASSEMBLED:
             names += [("spmv_assembled", 0), ("jacobian_fill", 3), ("pcg_iteration_assembled", 2), ("jacobian_per_element", 7)]
         if op == M.OP_ASSEMBLED_SYM:
-            names += [("spmv_sym", 8), ("pcg_iteration_sym", 9)]
+            # the per-element Jacobian kernel (uniform D from constant memory) into the symmetric layout
+            names += [("spmv_sym", 8), ("pcg_iteration_sym", 9), ("jacobian_per_element_sym", 17)]
         for name, what in names:
             m.time_kernel(what, 5)                          # 5 warm-ups, 20 timed launches, median
             kern[name] = max_over_ranks(statistics.median(m.time_kernel(what, 1) for _ in range(20)))
@@ -489,9 +490,16 @@ def run_gpu_arm(args):
                 pg = M.MacroC(M.Config(NX=g, NY=g, NZ=g, bc_type=M.BC_BENDING, device=local_rank, material=M.MAT_PER_GP,
                                        op=op if op != M.OP_MATRIX_FREE else M.OP_ASSEMBLED))
                 pg.apply_bc_on_u(-1e-3); pg.set_strains(); pg.homogenize()
-                pg.time_kernel(7, 2)
-                kern["jacobian_per_element_per_gp"] = statistics.median(pg.time_kernel(7, 1) for _ in range(5))
+                w_el = 17 if op == M.OP_ASSEMBLED_SYM else 7
+                pg.time_kernel(w_el, 2)
+                kern["jacobian_per_element_per_gp" + ("_sym" if w_el == 17 else "")] = statistics.median(pg.time_kernel(w_el, 1) for _ in range(5))
                 kern["residual_per_gp"] = statistics.median(pg.time_kernel(4, 1) for _ in range(5))
+                # north_star: "DMMA ... only if ncu shows a win over FFMA": the element contraction both ways, measured
+                ab = {"dmma_tflops_measured": pg.dmma_probe(), "elements": (g - 1) ** 3,
+                      "what": "Ke = sum_gp B^T C_gp B of every element from per-Gauss-point tangents (csrc/dmma_ab.cuh)"}
+                for v, nm in ((0, "dfma_sparsity_aware_ms"), (1, "dmma_dense_24_per_gp_ms"), (2, "dmma_upper_tiles_18_per_gp_ms")):
+                    ab[nm] = pg.contraction_ab(v, reps=3)[0]
+                other["contraction_ab"] = ab
                 pg.close()
             except Exception as exc:
                 kern["jacobian_per_element_per_gp"] = None
@@ -516,7 +524,7 @@ def run_gpu_arm(args):
         flops = 486.0 * (nloc / 3)
         achieved = flops / (apply_ms_max * 1e-3) / 1e12 if apply_ms_max > 0 else 0.0
         pk = fp64_tflops or 37.0
-        roof = {"bound": "fp64", "kernel": "k_apply_mf3d (matrix-free class-stencil apply)", "achieved": achieved,
+        roof = {"bound": "fp64", "kernel": "k_apply_mf_march (matrix-free class-stencil apply, z-marching)", "achieved": achieved,
                 "peak": pk, "unit": "TFLOP/s", "frac": achieved / pk,
                 "peak_source": "measured DFMA rate (macroc_fp64_probe)" if fp64_tflops else "nominal B200 fp64 (unmeasured)",
                 "launch_ms": apply_ms_max, "samples_in_timed_region": apply_samples, "traffic": None}
@@ -544,11 +552,16 @@ def run_gpu_arm(args):
         fp64 = {"dfma_tflops_measured": fp64_tflops, "how": "k_fp64_probe(_const): 16 independent DFMA chains per thread, 8 CTAs/SM, register and constant-bank multiplier, best of 2 x 5 launches"}
         if kern.get("apply_matrix_free"):
             fp64["apply_matrix_free_frac"] = 486.0 * nn / (kern["apply_matrix_free"] * 1e-3) / 1e12 / fp64_tflops
-        if kern.get("jacobian_per_element"):
-            fp64["jacobian_per_element_frac"] = 2 * 17280.0 * ne / (kern["jacobian_per_element"] * 1e-3) / 1e12 / fp64_tflops
-        if kern.get("jacobian_per_element_per_gp"):
-            fp64["jacobian_per_element_per_gp_frac"] = 2 * 17280.0 * ne / (kern["jacobian_per_element_per_gp"] * 1e-3) / 1e12 / fp64_tflops
-            fp64["jacobian_per_element_per_gp_hbm_frac"] = (72.0 * nb_local + 2304.0 * ne) / (kern["jacobian_per_element_per_gp"] * 1e-3) / 1e9 / peak
+        # element Jacobian: EXECUTED flops of the node-centric kernels (2 x 2112 FMA per node row entry set: 19 008 FMA per
+        # node in the full layout, 12 960 in the symmetric one) over the measured DFMA rate
+        nodes = nn
+        for key, fma_per_node in (("jacobian_per_element", 19008.0), ("jacobian_per_element_sym", 12960.0),
+                                  ("jacobian_per_element_per_gp", 19008.0), ("jacobian_per_element_per_gp_sym", 12960.0)):
+            if kern.get(key):
+                fp64[key + "_frac"] = 2 * fma_per_node * nodes / (kern[key] * 1e-3) / 1e12 / fp64_tflops
+        for key, stored in (("jacobian_per_element_per_gp", 72.0 * nb_local), ("jacobian_per_element_per_gp_sym", 36.0 * (nb_local + nn))):
+            if kern.get(key):
+                fp64[key + "_hbm_frac"] = (stored + 2304.0 * ne) / (kern[key] * 1e-3) / 1e9 / peak
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

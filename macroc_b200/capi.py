@@ -15,7 +15,7 @@ from dataclasses import dataclass
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-# MACROC_B200_LIB: an alternative build of the same library (measurement builds, tools/round2_open.sh)
+# MACROC_B200_LIB: an alternative build of the same library (measurement builds)
 LIB_PATH = os.environ.get("MACROC_B200_LIB") or os.path.join(HERE, "lib", "libmacroc_b200.so")
 CSRC = os.path.join(HERE, "csrc")
 

@@ -231,6 +231,7 @@ k_assemble_nodes_pergp(GridDev g, SymGeom sg, ElemRange er, double wg, const dou
     const int d = warp / 3, c = warp - 3 * d, e9 = warp;
     const int64_t per_layer = er.nex * er.ney;
     const double Cu[3][3] = {{0., 0., 0.}, {0., 0., 0.}, {0., 0., 0.}};
+    const uint64_t store_policy = l2_policy(0);
     int off[3][3];
 #pragma unroll
     for (int p = 0; p < 3; ++p)
@@ -269,13 +270,21 @@ k_assemble_nodes_pergp(GridDev g, SymGeom sg, ElemRange er, double wg, const dou
             cell_ie[threadIdx.x] = ie;
         }
         __syncthreads();
+        // staging plan: thread -> one cell and every second entry of it (threads 0..271; consecutive threads take
+        // consecutive cells = consecutive elements of a row: coalesced), so a copy costs an address increment
+        const int scell = threadIdx.x % ASMN_CELLS, shalf = threadIdx.x / ASMN_CELLS;            // shalf 2: idle
+        const int sie = cell_ie[scell];
         auto stage_gp = [&](int gp) {
-            double *dst = stage + (gp & 1) * ASMN_BUF_DOUBLES;
-            const double *src = ctan_gp + (int64_t)gp * 36 * er.ne_ext;
-            for (int q = threadIdx.x; q < ASMN_BUF_DOUBLES; q += ASMN_THREADS) {
-                const int entry = q / ASMN_CELLS, ie = cell_ie[q - entry * ASMN_CELLS];
-                if (ie >= 0) cp_async8(dst + q, src + (int64_t)entry * er.ne_ext + ie);
-                else dst[q] = 0.;
+            if (shalf < 2) {
+                double *dst = stage + (gp & 1) * ASMN_BUF_DOUBLES + shalf * ASMN_CELLS + scell;
+                if (sie >= 0) {
+                    const double *src = ctan_gp + ((int64_t)gp * 36 + shalf) * er.ne_ext + sie;
+#pragma unroll
+                    for (int q = 0; q < 18; ++q) cp_async8(dst + q * 2 * ASMN_CELLS, src + (int64_t)q * 2 * er.ne_ext);
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 18; ++q) dst[q * 2 * ASMN_CELLS] = 0.;
+                }
             }
             cp_async_commit();
         };
@@ -306,7 +315,9 @@ k_assemble_nodes_pergp(GridDev g, SymGeom sg, ElemRange er, double wg, const dou
         __syncthreads();
         if (threadIdx.x == 0) {
             double *dstp = reinterpret_cast<double *>(A) + tile * (int64_t)TILE_D;
-            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dstp), "r"(smem_u32(tileA)), "r"(TILE_D * 8)
+            // (evict-first: the finished tile must not push the tangents its neighbours still need out of L2)
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(dstp), "r"(smem_u32(tileA)),
+                         "r"(TILE_D * 8), "l"(store_policy)
                          : "memory");
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }

@@ -26,6 +26,7 @@
 #include "spmv_tma.cuh"
 #include "assembly_elem.cuh"
 #include "assembly_node.cuh"
+#include "mf_march.cuh"
 #include "dmma_ab.cuh"
 #include "spmv_sym.cuh"
 #include "loopback.h"
@@ -59,6 +60,7 @@ struct macroc_ctx {
     double2 *Asym = nullptr;         // symmetric storage (14 of 27 slots), MACROC_OP_ASSEMBLED_SYM; points at tile 0
     double2 *Asym_alloc = nullptr;   // start of the allocation: the ghost plane below (if any), then the slab
     SymGeom sg = {1, 0};
+    int mf_variant = 0, mf_nseg = 0;               // matrix-free apply: 0 z-marching (mf_march.cuh), 1 patch form; segments override (MACROC_MF_*)
     int asm_variant = 0, asm_colblock = 64, asm_ctas_per_sm = 2;   // element-Jacobian knobs (MACROC_ASM_*)
     int sym_R = 0, sym_nseg = 0, sym_variant = 0, sym_hint = 0;   // tuning overrides (MACROC_SYM_R / _NSEG / _VARIANT / _HINT, read once at create)
     bool A_valid = false, mf_ready = false, Asym_valid = false;
@@ -474,6 +476,8 @@ extern "C" int macroc_create(const macroc_config *cfg, int rank, int nranks, con
     if (const char *v = getenv("MACROC_SYM_NSEG")) c->sym_nseg = atoi(v);
     if (const char *v = getenv("MACROC_SYM_VARIANT")) c->sym_variant = atoi(v);
     if (const char *v = getenv("MACROC_SYM_HINT")) c->sym_hint = atoi(v);
+    if (const char *v = getenv("MACROC_MF_VARIANT")) c->mf_variant = atoi(v);
+    if (const char *v = getenv("MACROC_MF_NSEG")) c->mf_nseg = atoi(v);
     if (const char *v = getenv("MACROC_ASM_VARIANT")) c->asm_variant = atoi(v);
     if (const char *v = getenv("MACROC_ASM_COLBLOCK")) c->asm_colblock = atoi(v);
     if (const char *v = getenv("MACROC_ASM_CTAS")) c->asm_ctas_per_sm = atoi(v);
@@ -1209,6 +1213,31 @@ static int apply_operator(macroc_ctx *c, int op, double *p, double *w, bool with
                 default: blocks = spmv_sym_launch<8, 3, 8>(c, p, w, (int)first, (int)count, c->partial + nparts, with_dot, done); break;
             }
             if (blocks < 0) { rc_run = MACROC_ERR_CUDA; return; }
+        } else if (mf && c->mf_variant == 0) {
+            // z-marching form: work items = column blocks x z segments, dealt round-robin to the resident CTAs; pick the
+            // segment count whose slowest CTA marches through the fewest planes (a segment costs its planes + 2)
+            const int k0 = (int)(first / g.npl), k1 = (int)((first + count) / g.npl);
+            const int bx = (g.NX + MZ_BX - 1) / MZ_BX, by = (g.NY + MZ_BY - 1) / MZ_BY, nz = k1 - k0;
+            const int slots = 148 * 3;
+            int nseg = 1;
+            int64_t best = INT64_MAX;
+            for (int q = 1; q <= std::min(nz, 64); ++q) {
+                const int64_t items = (int64_t)bx * by * q, rounds = (items + slots - 1) / slots;
+                const int64_t cost = rounds * ((nz + q - 1) / q + 2);
+                if (cost < best) { best = cost; nseg = q; }
+            }
+            if (c->mf_nseg > 0) nseg = std::min(c->mf_nseg, nz);
+            blocks = (int)std::min<int64_t>((int64_t)bx * by * nseg, slots);
+            static bool mz_configured[64] = {false};
+            if (!mz_configured[c->device & 63]) {
+                cudaError_t e1 = cudaFuncSetAttribute(k_apply_mf_march<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MZ_SMEM);
+                cudaError_t e2 = cudaFuncSetAttribute(k_apply_mf_march<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MZ_SMEM);
+                if (e1 != cudaSuccess || e2 != cudaSuccess) { rc_run = MACROC_ERR_CUDA; return; }
+                mz_configured[c->device & 63] = true;
+            }
+            if (with_dot) k_apply_mf_march<true><<<blocks, MZ_THREADS, MZ_SMEM, c->stream>>>(g, c->T, c->nodemask, p, w, k0, k1, bx, by, nseg, c->partial + nparts, done);
+            else k_apply_mf_march<false><<<blocks, MZ_THREADS, MZ_SMEM, c->stream>>>(g, c->T, c->nodemask, p, w, k0, k1, bx, by, nseg, c->partial + nparts, done);
+            c->launches++;
         } else if (mf) {
             // node ranges are whole planes here
             const int k0 = (int)(first / g.npl), k1 = (int)((first + count) / g.npl);
