@@ -428,7 +428,7 @@ def run_gpu_arm(args):
             names += [("spmv_assembled", 0), ("jacobian_fill", 3), ("pcg_iteration_assembled", 2), ("jacobian_per_element", 7)]
         if op == M.OP_ASSEMBLED_SYM:
             # the per-element Jacobian kernel (uniform D from constant memory) into the symmetric layout
-            names += [("spmv_sym", 8), ("pcg_iteration_sym", 9), ("jacobian_per_element_sym", 17)]
+            names += [("spmv_sym", 8), ("pcg_iteration_sym", 9), ("jacobian_per_element_sym", 17), ("jacobian_per_element", 7)]
         for name, what in names:
             m.time_kernel(what, 5)                          # 5 warm-ups, 20 timed launches, median
             kern[name] = max_over_ranks(statistics.median(m.time_kernel(what, 1) for _ in range(20)))
@@ -471,7 +471,7 @@ def run_gpu_arm(args):
 
     # ---- BASELINE configs[1] (cantilever 128x32x32, lx=10 ly=lz=1) on one GPU, for the record ----
     if world == 1 and not args.no_extras:
-        c2 = M.MacroC(M.Config(NX=128, NY=32, NZ=32, lx=10., ly=1., lz=1., bc_type=M.BC_BENDING, device=local_rank))
+        c2 = M.MacroC(M.Config(NX=128, NY=32, NZ=32, lx=10., ly=1., lz=1., bc_type=M.BC_BENDING, device=local_rank, op=op))
         for t in (1, 2):
             c2.time_step(t)
         c2.event_record(0)
@@ -480,8 +480,20 @@ def run_gpu_arm(args):
         ms = c2.event_elapsed_ms(0, 1) / len(rs)
         other["cantilever_128x32x32"] = {"ndof": 393216, "ms_per_step": ms, "value": 393216 / (ms * 1e-3), "unit": UNIT,
                                          "cg_iterations_per_step": statistics.mean(sum(r["ksp_its"]) for r in rs),
-                                         "newton_its_per_step": [r["newton_its"] for r in rs]}
+                                         "newton_its_per_step": [r["newton_its"] for r in rs], "operator": op_name}
         c2.close()
+        if op != M.OP_MATRIX_FREE:
+            c2 = M.MacroC(M.Config(NX=128, NY=32, NZ=32, lx=10., ly=1., lz=1., bc_type=M.BC_BENDING, device=local_rank, op=M.OP_MATRIX_FREE))
+            for t in (1, 2):
+                c2.time_step(t)
+            c2.event_record(0)
+            rs = [c2.time_step(t) for t in (3, 4, 5, 6, 7)]
+            c2.event_record(1)
+            ms = c2.event_elapsed_ms(0, 1) / len(rs)
+            other["cantilever_128x32x32_matrix_free"] = {"ndof": 393216, "ms_per_step": ms, "value": 393216 / (ms * 1e-3), "unit": UNIT,
+                                                         "cg_iterations_per_step": statistics.mean(sum(r["ksp_its"]) for r in rs),
+                                                         "newton_its_per_step": [r["newton_its"] for r in rs], "operator": "matrix-free"}
+            c2.close()
         # the per-element Jacobian with a tangent per Gauss point (the north_star's assembly kernel) on the
         # workload grid: its own context (38 GB of tangents), uniform values written by the device stand-in
         if not args.no_kernels and not custom:
@@ -490,9 +502,9 @@ def run_gpu_arm(args):
                 pg = M.MacroC(M.Config(NX=g, NY=g, NZ=g, bc_type=M.BC_BENDING, device=local_rank, material=M.MAT_PER_GP,
                                        op=op if op != M.OP_MATRIX_FREE else M.OP_ASSEMBLED))
                 pg.apply_bc_on_u(-1e-3); pg.set_strains(); pg.homogenize()
-                w_el = 17 if op == M.OP_ASSEMBLED_SYM else 7
-                pg.time_kernel(w_el, 2)
-                kern["jacobian_per_element_per_gp" + ("_sym" if w_el == 17 else "")] = statistics.median(pg.time_kernel(w_el, 1) for _ in range(5))
+                for w_el, key in ((7, "jacobian_per_element_per_gp"), (17, "jacobian_per_element_per_gp_sym")):   # full / symmetric layout
+                    pg.time_kernel(w_el, 2)
+                    kern[key] = statistics.median(pg.time_kernel(w_el, 1) for _ in range(5))
                 kern["residual_per_gp"] = statistics.median(pg.time_kernel(4, 1) for _ in range(5))
                 # north_star: "DMMA ... only if ncu shows a win over FFMA": the element contraction both ways, measured
                 ab = {"dmma_tflops_measured": pg.dmma_probe(), "elements": (g - 1) ** 3,

@@ -24,7 +24,7 @@
 //    two warps that work on the same tile at the same time and meet in L2);
 //  * k_assemble_nodes_pergp -- tangents per Gauss point: one CTA of 9 warps per tile; the four element
 //    rows around the tile (33 elements each) are staged through shared memory one Gauss point ahead
-//    with cp.async (36 entries x 136 cells, two buffers), elements that do not exist are staged as zeros;
+//    with cp.async (36 entries x 132 cells, a ring of three buffers: one barrier per Gauss point), elements that do not exist are staged as zeros;
 //    the finished tile is laid out in the buffers in the operator's pair-interleaved order and leaves
 //    with ONE bulk copy (cp.async.bulk shared -> global, SASS UBLKCP).
 #pragma once
@@ -35,10 +35,11 @@ namespace macroc {
 
 constexpr int ASMN_WARPS = 9;
 constexpr int ASMN_THREADS = ASMN_WARPS * 32;
-constexpr int ASMN_SROW = 34;                               // staged elements per element row: 33 + 1 padding
+constexpr int ASMN_SROW = 33;                               // staged elements per element row
 constexpr int ASMN_CELLS = 4 * ASMN_SROW;                   // (ey, ez) in {j-1, j} x {k-1, k}
-constexpr int ASMN_BUF_DOUBLES = 36 * ASMN_CELLS;           // one Gauss point: 4 896 doubles
-constexpr int ASMN_SMEM_PER_GP = 2 * ASMN_BUF_DOUBLES * 8 + ASMN_CELLS * 4;   // 78 880 B: two CTAs per SM
+constexpr int ASMN_BUF_DOUBLES = 36 * ASMN_CELLS;           // one Gauss point: 4 752 doubles
+constexpr int ASMN_NBUF = 3;                                // ring: Gauss points gp, gp+1 resident or landing, gp+2 being issued
+constexpr int ASMN_SMEM_PER_GP = ASMN_NBUF * ASMN_BUF_DOUBLES * 8 + ASMN_CELLS * 4;   // 114 576 B: two CTAs per SM
 constexpr int ASMU_WARPS = 4, ASMU_CTAS_PER_SM = 5;         // uniform tangent: 20 independent warps per SM
 
 __host__ __device__ __forceinline__ constexpr int node_rank(int n) { return node_px(n) + 2 * node_py(n) + 4 * node_pz(n); }
@@ -224,9 +225,9 @@ k_assemble_nodes_pergp(GridDev g, SymGeom sg, ElemRange er, double wg, const dou
     constexpr int NS = SYM ? 14 : 27, S0 = SYM ? 13 : 0;
     constexpr int TILE_D = SYM ? SYM_TILE_DOUBLES : TILE_DOUBLES;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    double *stage = reinterpret_cast<double *>(smem_raw);                  // [2][36][ASMN_CELLS]
+    double *stage = reinterpret_cast<double *>(smem_raw);                  // [ASMN_NBUF][36][ASMN_CELLS]
     double *tileA = stage;                                                 // the outgoing tile re-uses the buffers
-    int *cell_ie = reinterpret_cast<int *>(smem_raw + 2 * ASMN_BUF_DOUBLES * 8);   // element of a cell, -1 = none
+    int *cell_ie = reinterpret_cast<int *>(smem_raw + ASMN_NBUF * ASMN_BUF_DOUBLES * 8);   // element of a cell, -1 = none
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int d = warp / 3, c = warp - 3 * d, e9 = warp;
     const int64_t per_layer = er.nex * er.ney;
@@ -259,7 +260,7 @@ k_assemble_nodes_pergp(GridDev g, SymGeom sg, ElemRange er, double wg, const dou
             // cell (row r4, x): the element whose lowest corner is the node ln0 - 1 + x - NX py - npl pz
             const int r4 = threadIdx.x / ASMN_SROW, x = threadIdx.x - r4 * ASMN_SROW;
             int ie = -1;
-            if (x < 33) {
+            {
                 const int64_t lc = t.ln0 - 1 + x - (int64_t)g.NX * (1 - (r4 & 1)) - g.npl * (1 - (r4 >> 1)) + 3 * g.npl;   // > 0
                 const int kc = (int)(lc / g.npl) - 3;
                 const int64_t inpl = lc - (int64_t)(kc + 3) * g.npl;
@@ -276,7 +277,7 @@ k_assemble_nodes_pergp(GridDev g, SymGeom sg, ElemRange er, double wg, const dou
         const int sie = cell_ie[scell];
         auto stage_gp = [&](int gp) {
             if (shalf < 2) {
-                double *dst = stage + (gp & 1) * ASMN_BUF_DOUBLES + shalf * ASMN_CELLS + scell;
+                double *dst = stage + (gp % ASMN_NBUF) * ASMN_BUF_DOUBLES + shalf * ASMN_CELLS + scell;
                 if (sie >= 0) {
                     const double *src = ctan_gp + ((int64_t)gp * 36 + shalf) * er.ne_ext + sie;
 #pragma unroll
@@ -289,6 +290,7 @@ k_assemble_nodes_pergp(GridDev g, SymGeom sg, ElemRange er, double wg, const dou
             cp_async_commit();
         };
         stage_gp(0);
+        stage_gp(1);
         unsigned own, colmask;
         asmn_masks<SYM>(g, nodemask, masksum, t.ln0, lane, valid, c, own, colmask);
         double acc[NS];
@@ -296,12 +298,13 @@ k_assemble_nodes_pergp(GridDev g, SymGeom sg, ElemRange er, double wg, const dou
         for (int s = 0; s < NS; ++s) acc[s] = 0.;
 #pragma unroll 1
         for (int gp = 0; gp < 8; ++gp) {
-            if (gp < 7) { stage_gp(gp + 1); asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+            if (gp < 7) asm volatile("cp.async.wait_group 1;" ::: "memory");
             else asm volatile("cp.async.wait_group 0;" ::: "memory");
-            __syncthreads();                                             // Gauss point gp is in
-            asmn_gauss_point<true, SYM, true>(gp, 0u, Cu, stage + (gp & 1) * ASMN_BUF_DOUBLES + lane, off, acc);
-            __syncthreads();                                             // its buffer may be refilled
+            __syncthreads();                                             // Gauss point gp is in; the buffer of gp-1 has been read
+            if (gp + 2 < 8) stage_gp(gp + 2);
+            asmn_gauss_point<true, SYM, true>(gp, 0u, Cu, stage + (gp % ASMN_NBUF) * ASMN_BUF_DOUBLES + lane, off, acc);
         }
+        __syncthreads();                                                 // the buffers become the outgoing tile
         const bool rowfixed = (own >> d) & 1u, ghost_plane = SYM && t.kl < 0;
 #pragma unroll
         for (int s = S0; s < 27; ++s) {

@@ -60,6 +60,9 @@ struct macroc_ctx {
     double2 *Asym = nullptr;         // symmetric storage (14 of 27 slots), MACROC_OP_ASSEMBLED_SYM; points at tile 0
     double2 *Asym_alloc = nullptr;   // start of the allocation: the ghost plane below (if any), then the slab
     SymGeom sg = {1, 0};
+    unsigned *tickets = nullptr;                   // [2] last-block tickets of the fused single-rank reductions
+    CgFuse fuse_pw = {nullptr, nullptr};           // set by apply_operator for the launch it is about to make
+    bool fuse_pw_done = false;
     int mf_variant = 0, mf_nseg = 0;               // matrix-free apply: 0 z-marching (mf_march.cuh), 1 patch form; segments override (MACROC_MF_*)
     int asm_variant = 0, asm_colblock = 64, asm_ctas_per_sm = 2;   // element-Jacobian knobs (MACROC_ASM_*)
     int sym_R = 0, sym_nseg = 0, sym_variant = 0, sym_hint = 0;   // tuning overrides (MACROC_SYM_R / _NSEG / _VARIANT / _HINT, read once at create)
@@ -367,7 +370,7 @@ static int ctx_free(macroc_ctx *c)
     }
     for (cudaGraphExec_t ge : c->cg_graph) if (ge) cudaGraphExecDestroy(ge);
     for (int i = 0; i < V_COUNT; ++i) cudaFree(c->vec[i]);
-    cudaFree(c->A); cudaFree(c->Asym_alloc); cudaFree(c->Ke); cudaFree(c->T); cudaFree(c->nodemask); cudaFree(c->masksum); cudaFree(c->bc_idx); cudaFree(c->bc_coef);
+    cudaFree(c->A); cudaFree(c->Asym_alloc); cudaFree(c->Ke); cudaFree(c->T); cudaFree(c->nodemask); cudaFree(c->masksum); cudaFree(c->tickets); cudaFree(c->bc_idx); cudaFree(c->bc_coef);
     cudaFree(c->partial); cudaFree(c->sums); cudaFree(c->sc); cudaFree(c->stage); cudaFree(c->strain); cudaFree(c->stress);
     cudaFree(c->ctan); cudaFree(c->scratch); cudaFree(c->consts); cudaFree(c->gp_halo); cudaFree(c->ghostflag); cudaFree(c->xy_halo);
     cudaFree(c->flush);
@@ -517,6 +520,8 @@ extern "C" int macroc_create(const macroc_config *cfg, int rank, int nranks, con
     c->spmv_blocks = std::min<int64_t>(cdiv64(g.ntiles, 8), 148 * 8);
     c->partial_cap = std::max<int64_t>({(int64_t)cdiv64(g.nloc, 128) + slab.nzl + 8, (int64_t)2 * c->vec_blocks, (int64_t)3 * c->spmv_blocks + 8, (int64_t)4096});
     CUC(cudaMalloc(&c->partial, sizeof(double) * c->partial_cap));
+    CUC(cudaMalloc(&c->tickets, 2 * sizeof(unsigned)));
+    CUC(cudaMemset(c->tickets, 0, 2 * sizeof(unsigned)));
 
     // element bookkeeping: DMDA-owned layers plus, for the gather-form assembly, the first layer
     // of the upper neighbour (integrated redundantly / received as Gauss-point halo)
@@ -1093,8 +1098,9 @@ static int spmv_launch_tma(macroc_ctx *c, double *p, double *w, int64_t first, i
     }
     int per_sm = std::max(1, (227 * 1024) / (SM::total + 1024));
     int blocks = (int)std::min<int64_t>(cdiv64(count, WARPS), (int64_t)148 * per_sm);
-    if (with_dot) k_spmv_tma<WARPS, NSTAGE, true><<<blocks, WARPS * 32, SM::total, c->stream>>>(c->g, c->A, p, w, first, count, partial, done);
-    else k_spmv_tma<WARPS, NSTAGE, false><<<blocks, WARPS * 32, SM::total, c->stream>>>(c->g, c->A, p, w, first, count, partial, done);
+    if (with_dot) k_spmv_tma<WARPS, NSTAGE, true><<<blocks, WARPS * 32, SM::total, c->stream>>>(c->g, c->A, p, w, first, count, partial, done, c->fuse_pw);
+    else k_spmv_tma<WARPS, NSTAGE, false><<<blocks, WARPS * 32, SM::total, c->stream>>>(c->g, c->A, p, w, first, count, partial, done, CgFuse{nullptr, nullptr});
+    if (with_dot && c->fuse_pw.ticket) c->fuse_pw_done = true;
     c->launches++;
     return blocks;
 }
@@ -1155,8 +1161,9 @@ static int spmv_sym_launch(macroc_ctx *c, double *p, double *w, int first, int c
     }
     const int64_t bands = (int64_t)c->sg.rt * ((g.NY + R - 1) / R);
     const int blocks = (int)std::min<int64_t>(cdiv64(bands * nseg, WARPS), 148);
-    if (with_dot) k_spmv_sym<WARPS, NSTAGE, RMAX, true><<<blocks, WARPS * 32, SM::total, c->stream>>>(g, c->sg, c->Asym, p, w, first, first + count, R, nseg, partial, done, c->sym_hint);
-    else k_spmv_sym<WARPS, NSTAGE, RMAX, false><<<blocks, WARPS * 32, SM::total, c->stream>>>(g, c->sg, c->Asym, p, w, first, first + count, R, nseg, partial, done, c->sym_hint);
+    if (with_dot) k_spmv_sym<WARPS, NSTAGE, RMAX, true><<<blocks, WARPS * 32, SM::total, c->stream>>>(g, c->sg, c->Asym, p, w, first, first + count, R, nseg, partial, done, c->sym_hint, c->fuse_pw);
+    else k_spmv_sym<WARPS, NSTAGE, RMAX, false><<<blocks, WARPS * 32, SM::total, c->stream>>>(g, c->sg, c->Asym, p, w, first, first + count, R, nseg, partial, done, c->sym_hint, CgFuse{nullptr, nullptr});
+    if (with_dot && c->fuse_pw.ticket) c->fuse_pw_done = true;
     c->launches++;
     return blocks;
 }
@@ -1196,6 +1203,9 @@ static int apply_operator(macroc_ctx *c, int op, double *p, double *w, bool with
         }
     }
     int nparts = 0, rc_run = MACROC_OK;
+    // single rank, one launch: the kernel's last block folds the p.w partials and updates the CG scalars itself
+    c->fuse_pw_done = false;
+    c->fuse_pw = (with_dot && fuse_pw_scalars && !nparts_out && !split) ? CgFuse{c->sc, c->tickets} : CgFuse{nullptr, nullptr};
     auto run = [&](int64_t first, int64_t count) {
         if (count <= 0) return;
         int blocks;
@@ -1235,9 +1245,20 @@ static int apply_operator(macroc_ctx *c, int op, double *p, double *w, bool with
                 if (e1 != cudaSuccess || e2 != cudaSuccess) { rc_run = MACROC_ERR_CUDA; return; }
                 mz_configured[c->device & 63] = true;
             }
-            if (with_dot) k_apply_mf_march<true><<<blocks, MZ_THREADS, MZ_SMEM, c->stream>>>(g, c->T, c->nodemask, p, w, k0, k1, bx, by, nseg, c->partial + nparts, done);
-            else k_apply_mf_march<false><<<blocks, MZ_THREADS, MZ_SMEM, c->stream>>>(g, c->T, c->nodemask, p, w, k0, k1, bx, by, nseg, c->partial + nparts, done);
+            // the nodes on a face of the box first (their partials come first), then the marching kernel for the rest
+            const int64_t nface = mf_face_count(g, k0, k1);
+            const int fblocks = (int)std::min<int64_t>(cdiv64(nface, 128), 148 * 8);
+            double *pbase = c->partial + nparts;
+            if (fblocks > 0) {
+                if (with_dot) k_apply_mf_faces<true><<<fblocks, 128, 0, c->stream>>>(g, c->T, c->nodemask, p, w, k0, k1, pbase, done);
+                else k_apply_mf_faces<false><<<fblocks, 128, 0, c->stream>>>(g, c->T, c->nodemask, p, w, k0, k1, pbase, done);
+                c->launches++;
+            }
+            if (with_dot) k_apply_mf_march<true><<<blocks, MZ_THREADS, MZ_SMEM, c->stream>>>(g, c->T, c->nodemask, p, w, k0, k1, bx, by, nseg, pbase, fblocks, done, c->fuse_pw);
+            else k_apply_mf_march<false><<<blocks, MZ_THREADS, MZ_SMEM, c->stream>>>(g, c->T, c->nodemask, p, w, k0, k1, bx, by, nseg, pbase, fblocks, done, CgFuse{nullptr, nullptr});
+            if (with_dot && c->fuse_pw.ticket) c->fuse_pw_done = true;
             c->launches++;
+            blocks += fblocks;
         } else if (mf) {
             // node ranges are whole planes here
             const int k0 = (int)(first / g.npl), k1 = (int)((first + count) / g.npl);
@@ -1268,10 +1289,11 @@ static int apply_operator(macroc_ctx *c, int op, double *p, double *w, bool with
         run(hi_begin, total - hi_begin);
     } else
         run(0, total);
+    c->fuse_pw = CgFuse{nullptr, nullptr};
     if (rc_run) FAIL(c, rc_run, "apply_operator: kernel configuration failed (shared memory)");
     if (with_dot) {
         if (nparts_out) *nparts_out = nparts;        // the caller folds the partials (mailbox all-reduce kernel)
-        else if (fuse_pw_scalars) LAUNCH(c, k_cg_reduce_pw, 1, 256, c->partial, nparts, c->sc);
+        else if (fuse_pw_scalars) { if (!c->fuse_pw_done) LAUNCH(c, k_cg_reduce_pw, 1, 256, c->partial, nparts, c->sc); }
         else LAUNCH(c, k_reduce, 1, 256, c->partial, nparts, c->sums);
     }
     CU(c, cudaGetLastError());
@@ -1316,9 +1338,10 @@ static int cg_iteration(macroc_ctx *c, int op)
         if (rc) return rc;
         LAUNCH(c, k_cg_scalars_pw, 1, 1, c->sc, c->sums);
     }
-    LAUNCH(c, k_cg_update_xr, nb, 256, g, c->sc, c->vec[V_P], c->vec[V_W], c->vec[V_DINV], c->vec[V_DU], c->vec[V_R], c->partial, nb);
+    LAUNCH(c, k_cg_update_xr, nb, 256, g, c->sc, c->vec[V_P], c->vec[V_W], c->vec[V_DINV], c->vec[V_DU], c->vec[V_R], c->partial, nb,
+           single ? CgFuse{c->sc, c->tickets + 1} : CgFuse{nullptr, nullptr});
     if (single) {
-        LAUNCH(c, k_cg_reduce_iter, 1, 256, c->partial, nb, c->sc);
+        // (z.z, z.r) and the convergence test: folded by the last block of k_cg_update_xr
     } else if (c->mbox_on) {
         LAUNCH(c, k_cg_reduce_iter_mbox, 1, 256, c->partial, nb, c->sc, mb, ++c->mbox_seq);
     } else {

@@ -9,8 +9,12 @@
 // (output-stationary, 36 accumulators).  Per step and thread: 54 shared-memory loads and 135 128-bit
 // constant-bank loads feed 972 FMA -- a 3 x 3 stencil block is loaded once and used for the four nodes -- where
 // the patch form of kernels.cuh (k_apply_mf3d: input-stationary, two CTA barriers around a 52 KB stage) needs
-// 162 + 486.  Every x value leaves HBM once per column block.  Interior warps take the stencil entries from the
-// constant bank; warps with a node on a face read the class tables from global memory (L1 resident).
+// 162 + 486.  Every x value leaves HBM once per column block.  The marching kernel knows one stencil only, the
+// interior class, taken from the constant bank; the nodes on a face of the box (2.3 % at 256^3: their rows sum fewer
+// elements, 26 other classes) are skipped by it and done by k_apply_mf_faces, one thread per node, class table
+// from global memory.  (A per-lane class inside the marching loop cost more than everything else: a fifth of
+// the warps held a face node and ran a 972-load path 5.8 times slower than their neighbours, who waited for
+// them at the barrier -- ncu, profiles/r2_mf_history.md.)
 #pragma once
 
 #include "kernels.cuh"
@@ -33,8 +37,8 @@ constexpr int MZ_SMEM = MZ_SLOTS * MZ_SLOT_BYTES;          // 61 312 B: three CT
 template <bool DOT>
 __global__ void __launch_bounds__(MZ_THREADS, 3)
 k_apply_mf_march(GridDev g, const double *__restrict__ Tg, const uint8_t *__restrict__ nodemask, const double *__restrict__ x,
-                 double *__restrict__ y, int k0, int k1, int bx, int by, int nseg, double *__restrict__ partial,
-                 const int *__restrict__ done)
+                 double *__restrict__ y, int k0, int k1, int bx, int by, int nseg, double *__restrict__ partial /* all partials of this apply */,
+                 int part0 /* this kernel's first slot in it (the face kernel's come before) */, const int *__restrict__ done, CgFuse fuse)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     auto sxp = [&](int slot, int comp) -> double * { return reinterpret_cast<double *>(smem_raw + slot * MZ_SLOT_BYTES) + comp * MZ_PLANE; };
@@ -53,15 +57,10 @@ k_apply_mf_march(GridDev g, const double *__restrict__ Tg, const uint8_t *__rest
         const int zlo = k0 + seg * seglen, zhi = min(k1, zlo + seglen);          // slab-local output planes [zlo, zhi)
         if (zlo >= zhi) continue;                                                  // block-uniform
         const int i = i0 + tx, jb = j0 + ty0;
-        const int cx = node_class(i, g.NX);
-        bool xy_interior = i < g.NX ? cx == 1 : true;
-        int cxy[MZ_NY];
+        // nodes on an x or y face of the box belong to k_apply_mf_faces
+        bool face_xy[MZ_NY];
 #pragma unroll
-        for (int jj = 0; jj < MZ_NY; ++jj) {
-            const bool v = i < g.NX && jb + jj < g.NY;
-            cxy[jj] = v ? cx + 3 * node_class(jb + jj, g.NY) : 4;
-            xy_interior = xy_interior && cxy[jj] == 4;
-        }
+        for (int jj = 0; jj < MZ_NY; ++jj) face_xy[jj] = i == 0 || i == g.NX - 1 || jb + jj == 0 || jb + jj == g.NY - 1;
         // staging: plane s -> slot.  The Dirichlet bytes of this thread's points are loaded into registers and first
         // looked at one step later (an immediate use would expose the load latency once per step).
         unsigned mkb[MZ_NIT];
@@ -121,64 +120,30 @@ k_apply_mf_march(GridDev g, const double *__restrict__ Tg, const uint8_t *__rest
             if (s + 1 <= zhi) mask_plane((s + 5) % MZ_SLOTS);
             __syncthreads();                               // planes s and s+1 are complete; the slot of plane s-2 has been read
             if (s + 2 <= zhi) stage_plane(s + 2, (s + 6) % MZ_SLOTS);
-            // classes of the three output planes (global z = slab-local + zs); planes outside the grid are never written
-            const int zg = s + g.zs;
-            const int czm = 9 * node_class(zg - 1, g.NZ), czc = 9 * node_class(zg, g.NZ), czp = 9 * node_class(zg + 1, g.NZ);
-            const bool interior = xy_interior && czm == 9 && czc == 9 && czp == 9;
             const double *s0 = sxp(cur, 0) + cb, *s1 = sxp(cur, 1) + cb, *s2 = sxp(cur, 2) + cb;
-            if (__all_sync(0xffffffffu, interior)) {
 #pragma unroll
-                for (int dx = -1; dx <= 1; ++dx) {
-                    double xr[MZ_NY + 2][3];               // the six rows this thread's nodes see at this dx
+            for (int dx = -1; dx <= 1; ++dx) {
+                double xr[MZ_NY + 2][3];               // the six rows this thread's nodes see at this dx
 #pragma unroll
-                    for (int py = 0; py < MZ_NY + 2; ++py) {
-                        const int o = (py - 1) * MZ_PITCH + dx;
-                        xr[py][0] = s0[o]; xr[py][1] = s1[o]; xr[py][2] = s2[o];
-                    }
-#pragma unroll
-                    for (int dy = -1; dy <= 1; ++dy) {
-                        const int sl = ((dy + 1) * 3 + (dx + 1)) * 9;
-                        constexpr int base = 13 * 243;
-#pragma unroll
-                        for (int r = 0; r < 3; ++r) {
-                            const double p0 = c_T[base + sl + 3 * r], p1 = c_T[base + sl + 3 * r + 1], p2 = c_T[base + sl + 3 * r + 2];
-                            const double c0 = c_T[base + 81 + sl + 3 * r], c1 = c_T[base + 81 + sl + 3 * r + 1], c2 = c_T[base + 81 + sl + 3 * r + 2];
-                            const double m0 = c_T[base + 162 + sl + 3 * r], m1 = c_T[base + 162 + sl + 3 * r + 1], m2 = c_T[base + 162 + sl + 3 * r + 2];
-#pragma unroll
-                            for (int jj = 0; jj < MZ_NY; ++jj) {
-                                const double x0 = xr[jj + 1 + dy][0], x1 = xr[jj + 1 + dy][1], x2 = xr[jj + 1 + dy][2];
-                                ap[jj][r] = fma(p2, x2, fma(p1, x1, fma(p0, x0, ap[jj][r])));
-                                ac[jj][r] = fma(c2, x2, fma(c1, x1, fma(c0, x0, ac[jj][r])));
-                                am[jj][r] = fma(m2, x2, fma(m1, x1, fma(m0, x0, am[jj][r])));
-                            }
-                        }
-                    }
+                for (int py = 0; py < MZ_NY + 2; ++py) {
+                    const int o = (py - 1) * MZ_PITCH + dx;
+                    xr[py][0] = s0[o]; xr[py][1] = s1[o]; xr[py][2] = s2[o];
                 }
-            } else {
-                // boundary classes: per-node class offsets into the global copy of the table (L1 resident; lanes of
-                // one class broadcast, divergent constant-bank reads would serialise)
-#pragma unroll 1
-                for (int dx = -1; dx <= 1; ++dx) {
-                    double xr[MZ_NY + 2][3];
 #pragma unroll
-                    for (int py = 0; py < MZ_NY + 2; ++py) {
-                        const int o = (py - 1) * MZ_PITCH + dx;
-                        xr[py][0] = s0[o]; xr[py][1] = s1[o]; xr[py][2] = s2[o];
-                    }
+                for (int dy = -1; dy <= 1; ++dy) {
+                    const int sl = ((dy + 1) * 3 + (dx + 1)) * 9;
+                    constexpr int base = 13 * 243;
 #pragma unroll
-                    for (int dy = -1; dy <= 1; ++dy) {
-                        const int sl = ((dy + 1) * 3 + (dx + 1)) * 9;
+                    for (int r = 0; r < 3; ++r) {
+                        const double p0 = c_T[base + sl + 3 * r], p1 = c_T[base + sl + 3 * r + 1], p2 = c_T[base + sl + 3 * r + 2];
+                        const double c0 = c_T[base + 81 + sl + 3 * r], c1 = c_T[base + 81 + sl + 3 * r + 1], c2 = c_T[base + 81 + sl + 3 * r + 2];
+                        const double m0 = c_T[base + 162 + sl + 3 * r], m1 = c_T[base + 162 + sl + 3 * r + 1], m2 = c_T[base + 162 + sl + 3 * r + 2];
 #pragma unroll
                         for (int jj = 0; jj < MZ_NY; ++jj) {
-                            const double *Tp = Tg + (cxy[jj] + czp) * 243 + sl, *Tc = Tg + (cxy[jj] + czc) * 243 + 81 + sl,
-                                         *Tm = Tg + (cxy[jj] + czm) * 243 + 162 + sl;
                             const double x0 = xr[jj + 1 + dy][0], x1 = xr[jj + 1 + dy][1], x2 = xr[jj + 1 + dy][2];
-#pragma unroll
-                            for (int r = 0; r < 3; ++r) {
-                                ap[jj][r] = fma(__ldg(Tp + 3 * r + 2), x2, fma(__ldg(Tp + 3 * r + 1), x1, fma(__ldg(Tp + 3 * r), x0, ap[jj][r])));
-                                ac[jj][r] = fma(__ldg(Tc + 3 * r + 2), x2, fma(__ldg(Tc + 3 * r + 1), x1, fma(__ldg(Tc + 3 * r), x0, ac[jj][r])));
-                                am[jj][r] = fma(__ldg(Tm + 3 * r + 2), x2, fma(__ldg(Tm + 3 * r + 1), x1, fma(__ldg(Tm + 3 * r), x0, am[jj][r])));
-                            }
+                            ap[jj][r] = fma(p2, x2, fma(p1, x1, fma(p0, x0, ap[jj][r])));
+                            ac[jj][r] = fma(c2, x2, fma(c1, x1, fma(c0, x0, ac[jj][r])));
+                            am[jj][r] = fma(m2, x2, fma(m1, x1, fma(m0, x0, am[jj][r])));
                         }
                     }
                 }
@@ -186,9 +151,11 @@ k_apply_mf_march(GridDev g, const double *__restrict__ Tg, const uint8_t *__rest
             if (s - 1 >= zlo && i < g.NX) {                // plane s-1 has all three contributions (s-1 < zhi always)
                 const double *q0 = sxp(prv, 0) + cb, *q1 = sxp(prv, 1) + cb, *q2 = sxp(prv, 2) + cb;   // M x of plane s-1 (still resident)
                 const uint8_t *qm = smk(prv) + cb;
+                const int zgm = s - 1 + g.zs;
+                const bool zface = zgm == 0 || zgm == g.NZ - 1;
 #pragma unroll
                 for (int jj = 0; jj < MZ_NY; ++jj) {
-                    if (jb + jj >= g.NY) continue;
+                    if (jb + jj >= g.NY || face_xy[jj] || zface) continue;
                     const int64_t ln = (int64_t)(s - 1) * g.npl + (int64_t)(jb + jj) * g.NX + i;
                     const unsigned own = qm[jj * MZ_PITCH];
                     double a0 = am[jj][0], a1 = am[jj][1], a2 = am[jj][2];
@@ -212,6 +179,80 @@ k_apply_mf_march(GridDev g, const double *__restrict__ Tg, const uint8_t *__rest
     }
     if (DOT) {
         double s = block_sum<MZ_THREADS / 32>(dot, sm);
+        if (threadIdx.x == 0) partial[part0 + blockIdx.x] = s;
+        if (fuse.ticket) cg_last_block<MZ_THREADS / 32, 1>(partial, part0 + gridDim.x, fuse, sm);
+    }
+}
+
+// The nodes on a face of the box, planes [k0, k1): x faces (all their nodes), y faces (without the x-face nodes),
+// global z faces (without both).  One thread per node, its class stencil from the global table.
+__host__ __device__ __forceinline__ int64_t mf_face_count(const GridDev &g, int k0, int k1)
+{
+    const int64_t nzp = k1 - k0, nx2 = g.NX > 2 ? g.NX - 2 : 0, ny2 = g.NY > 2 ? g.NY - 2 : 0;
+    const int zf = (k0 + g.zs <= 0 && 0 < k1 + g.zs ? 1 : 0) + (g.NZ > 1 && k0 + g.zs <= g.NZ - 1 && g.NZ - 1 < k1 + g.zs ? 1 : 0);
+    return (g.NX > 1 ? 2 : 1) * (int64_t)g.NY * nzp + (g.NY > 1 ? 2 : 1) * nx2 * nzp + zf * nx2 * ny2;
+}
+
+template <bool DOT>
+__global__ void __launch_bounds__(128)
+k_apply_mf_faces(GridDev g, const double *__restrict__ Tg, const uint8_t *__restrict__ nodemask, const double *__restrict__ x,
+                 double *__restrict__ y, int k0, int k1, double *__restrict__ partial, const int *__restrict__ done)
+{
+    __shared__ double sm[4];
+    if (done && *done) return;
+    const int64_t nzp = k1 - k0, nx2 = g.NX > 2 ? g.NX - 2 : 0, ny2 = g.NY > 2 ? g.NY - 2 : 0;
+    const int sxn = g.NX > 1 ? 2 : 1, syn = g.NY > 1 ? 2 : 1;
+    const int64_t nA = sxn * (int64_t)g.NY * nzp, nB = syn * nx2 * nzp, total = mf_face_count(g, k0, k1);
+    const bool zlow = k0 + g.zs <= 0 && 0 < k1 + g.zs;
+    double dot = 0.;
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (int64_t)gridDim.x * blockDim.x) {
+        int i, j, kl;
+        if (q < nA) {
+            const int64_t per = (int64_t)g.NY * nzp;
+            const int side = (int)(q / per); const int64_t r = q - side * per;
+            i = side ? g.NX - 1 : 0; j = (int)(r % g.NY); kl = k0 + (int)(r / g.NY);
+        } else if (q < nA + nB) {
+            const int64_t qq = q - nA, per = nx2 * nzp;
+            const int side = (int)(qq / per); const int64_t r = qq - side * per;
+            j = side ? g.NY - 1 : 0; i = 1 + (int)(r % nx2); kl = k0 + (int)(r / nx2);
+        } else {
+            const int64_t qq = q - nA - nB, per = nx2 * ny2;
+            const int side = (int)(qq / per); const int64_t r = qq - side * per;
+            kl = (side == 0 && zlow) ? -g.zs : g.NZ - 1 - g.zs;
+            i = 1 + (int)(r % nx2); j = 1 + (int)(r / nx2);
+        }
+        const int64_t ln = (int64_t)kl * g.npl + (int64_t)j * g.NX + i;
+        const int type = node_class(i, g.NX) + 3 * node_class(j, g.NY) + 9 * node_class(kl + g.zs, g.NZ);
+        const double *Tt = Tg + type * 243;
+        double a0 = 0., a1 = 0., a2 = 0.;
+#pragma unroll 1
+        for (int sl = 0; sl < 27; ++sl) {
+            const int dx = sl % 3 - 1, dy = (sl / 3) % 3 - 1, dz = sl / 9 - 1;
+            const int64_t lj = ln + dx + (int64_t)g.NX * dy + g.npl * dz;
+            const bool ok = i + dx >= -1 && i + dx <= g.NX && lj >= -(int64_t)g.G && g.G + lj < g.S;
+            double x0 = 0., x1 = 0., x2 = 0.;
+            if (ok) {
+                const unsigned mk = nodemask[g.G + lj];
+                const double *xp = x + g.G + lj;
+                x0 = (mk & 1u) ? 0. : __ldg(xp); x1 = (mk & 2u) ? 0. : __ldg(xp + g.S); x2 = (mk & 4u) ? 0. : __ldg(xp + 2 * g.S);
+            }
+            const double *m = Tt + sl * 9;
+            a0 = fma(__ldg(m + 2), x2, fma(__ldg(m + 1), x1, fma(__ldg(m + 0), x0, a0)));
+            a1 = fma(__ldg(m + 5), x2, fma(__ldg(m + 4), x1, fma(__ldg(m + 3), x0, a1)));
+            a2 = fma(__ldg(m + 8), x2, fma(__ldg(m + 7), x1, fma(__ldg(m + 6), x0, a2)));
+        }
+        const unsigned own = nodemask[g.G + ln];
+        const double *xo = x + g.G + ln;
+        const double p0 = __ldg(xo), p1 = __ldg(xo + g.S), p2 = __ldg(xo + 2 * g.S);
+        if (own & 1u) a0 = p0;                              // Dirichlet rows are identity rows
+        if (own & 2u) a1 = p1;
+        if (own & 4u) a2 = p2;
+        double *y0 = y + g.G + ln;
+        y0[0] = a0; y0[g.S] = a1; y0[2 * g.S] = a2;
+        if (DOT && owned_node(g, ln)) dot += a0 * p0 + a1 * p1 + a2 * p2;
+    }
+    if (DOT) {
+        double s = block_sum<4>(dot, sm);
         if (threadIdx.x == 0) partial[blockIdx.x] = s;
     }
 }

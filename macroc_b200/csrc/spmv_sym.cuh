@@ -186,7 +186,8 @@ template <int WARPS, int NSTAGE, int RMAX, bool DOT>
 __global__ void __launch_bounds__(WARPS * 32, 1)
 k_spmv_sym(GridDev g, SymGeom sg, const double2 *__restrict__ A, const double *__restrict__ p, double *__restrict__ w,
            int zA, int zB, int R, int nseg, double *__restrict__ partial, const int *__restrict__ done,
-           int hint /* L2 policies, 2 bits each: [1:0] operator stream (0 evict_first), [3:2] vector loads (0 default) */)
+           int hint /* L2 policies, 2 bits each: [1:0] operator stream (0 evict_first), [3:2] vector loads (0 default) */,
+           CgFuse fuse /* single rank: the last block folds the partials and updates the CG scalars */)
 {
     using SM = SpmvSymSmem<WARPS, NSTAGE, RMAX>;
     extern __shared__ __align__(128) unsigned char smem_ring[];
@@ -449,6 +450,7 @@ k_spmv_sym(GridDev g, SymGeom sg, const double2 *__restrict__ A, const double *_
             for (int qq = 0; qq < WARPS; ++qq) s += red[qq];
             partial[blockIdx.x] = s;
         }
+        if (fuse.ticket) cg_last_block<WARPS, 1>(partial, gridDim.x, fuse, red);
     }
 }
 

@@ -74,7 +74,7 @@ struct SpmvTmaSmem {
 template <int WARPS, int NSTAGE, bool DOT>
 __global__ void __launch_bounds__(WARPS * 32, 1)
 k_spmv_tma(GridDev g, const double2 *__restrict__ A, const double *__restrict__ p, double *__restrict__ w,
-           int64_t tile0, int64_t ntiles, double *__restrict__ partial, const int *__restrict__ done)
+           int64_t tile0, int64_t ntiles, double *__restrict__ partial, const int *__restrict__ done, CgFuse fuse)
 {
     static_assert(NSTAGE >= 2 && NSTAGE < CHUNKS_PER_TILE, "ring depth");
     extern __shared__ __align__(128) unsigned char smem_ring[];
@@ -174,6 +174,7 @@ k_spmv_tma(GridDev g, const double2 *__restrict__ A, const double *__restrict__ 
             for (int q = 0; q < WARPS; ++q) s += red[q];
             partial[blockIdx.x] = s;
         }
+        if (fuse.ticket) cg_last_block<WARPS, 1>(partial, gridDim.x, fuse, red);
     }
 }
 

@@ -262,6 +262,32 @@ def test_large_grid_properties():
     assert np.isfinite(du).all()
 
 
+def test_large_grid_element_kernels_and_operators_agree():
+    """Full width (256 x 256 nodes per plane, 24 planes: 1.6 M nodes, every tile class of the 256^3 workload) --
+    the node-centric element kernels (uniform tangent and per-Gauss-point tangents) against the class-stencil
+    fill, which is bitwise the oracle's operator on every grid the oracle can hold; the symmetric storage, the
+    full storage and the z-marching matrix-free operator applied to the same vector."""
+    kw = dict(NX=256, NY=256, NZ=24, bc_type=M.BC_BENDING)
+    rng = np.random.default_rng(23)
+    ref = M.MacroC(M.Config(**kw)); ref.assembly_jac()
+    A_ref = ref.get_matrix_blocks()
+    x = rng.standard_normal(ref.local_ndof)
+    Ax = ref.matmult(x)
+    assert rel_err(ref.matmult(x, M.OP_MATRIX_FREE), Ax) < 1e-13
+    ref.close()
+    scale = np.abs(A_ref).max()
+    for material in (M.MAT_UNIFORM, M.MAT_PER_GP):
+        for op in (M.OP_ASSEMBLED, M.OP_ASSEMBLED_SYM):
+            m = M.MacroC(M.Config(material=material, jac_mode=M.JAC_ELEMENT, op=op, **kw))
+            m.set_strains(); m.homogenize(); m.assembly_jac()
+            lo = 13 if op == M.OP_ASSEMBLED_SYM else 0
+            A = m.get_matrix_blocks()
+            assert np.abs(A[:, lo:] - A_ref[:, lo:]).max() < TOL_MAT * scale, (material, op)
+            del A
+            assert rel_err(m.matmult(x, op), Ax) < 1e-12
+            m.close()
+
+
 @pytest.mark.parametrize("name", ["readme_4x4x2_bending", "ctest_4x4x4_circle", "beam_16x6x6_bending"])
 def test_c_host_driver_log_matches_reference(name, tmp_path):
     """macroc_b200/lib/macroc (the C host over the C ABI) prints the reference's lines."""
