@@ -24,7 +24,7 @@
 //    two warps that work on the same tile at the same time and meet in L2);
 //  * k_assemble_nodes_pergp -- tangents per Gauss point: one CTA of 9 warps per tile; the four element
 //    rows around the tile (33 elements each) are staged through shared memory one Gauss point ahead
-//    with cp.async (36 entries x 132 cells, a ring of three buffers: one barrier per Gauss point), elements that do not exist are staged as zeros;
+//    with cp.async (36 entries x 132 cells, two buffers), elements that do not exist are staged as zeros;
 //    the finished tile is laid out in the buffers in the operator's pair-interleaved order and leaves
 //    with ONE bulk copy (cp.async.bulk shared -> global, SASS UBLKCP).
 #pragma once
@@ -38,8 +38,9 @@ constexpr int ASMN_THREADS = ASMN_WARPS * 32;
 constexpr int ASMN_SROW = 33;                               // staged elements per element row
 constexpr int ASMN_CELLS = 4 * ASMN_SROW;                   // (ey, ez) in {j-1, j} x {k-1, k}
 constexpr int ASMN_BUF_DOUBLES = 36 * ASMN_CELLS;           // one Gauss point: 4 752 doubles
-constexpr int ASMN_NBUF = 3;                                // ring: Gauss points gp, gp+1 resident or landing, gp+2 being issued
-constexpr int ASMN_SMEM_PER_GP = ASMN_NBUF * ASMN_BUF_DOUBLES * 8 + ASMN_CELLS * 4;   // 114 576 B: two CTAs per SM
+constexpr int ASMN_NBUF = 2;                                // Gauss point gp is integrated while gp+1 lands.  (A ring of three with one barrier
+                                                            // per Gauss point needs 114.6 KB: one CTA per SM, 74 ms instead of 51.5.)
+constexpr int ASMN_SMEM_PER_GP = ASMN_NBUF * ASMN_BUF_DOUBLES * 8 + ASMN_CELLS * 4;   // 76 560 B: two CTAs per SM
 constexpr int ASMU_WARPS = 4, ASMU_CTAS_PER_SM = 5;         // uniform tangent: 20 independent warps per SM
 
 __host__ __device__ __forceinline__ constexpr int node_rank(int n) { return node_px(n) + 2 * node_py(n) + 4 * node_pz(n); }
@@ -166,7 +167,9 @@ k_assemble_nodes_uniform(GridDev g, SymGeom sg, ElemRange er, double wg, const u
     const int64_t gw = (int64_t)blockIdx.x * ASMU_WARPS + (threadIdx.x >> 5), nw = (int64_t)gridDim.x * ASMU_WARPS;
     const int64_t njobs = (tile_hi - tile_lo) * 9;
     const int off[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
-    // job = (tile, d, c); the nine jobs of a tile run on nine warps at the same time (consecutive warp ids)
+    // job = (tile, d, c); the nine jobs of a tile run on nine warps at the same time (consecutive warp ids).
+    // (All jobs take the same time; starting the CTAs of an SM a fifth of a job apart to keep their warps out of
+    // phase changed nothing: 25.43 -> 25.44 ms.)
     for (int64_t job = gw; job < njobs; job += nw) {
         const int64_t tq = job / 9, tile = tile_lo + tq;
         const int e9 = (int)(job - tq * 9), d = e9 / 3, c = e9 - 3 * d;
@@ -290,7 +293,6 @@ k_assemble_nodes_pergp(GridDev g, SymGeom sg, ElemRange er, double wg, const dou
             cp_async_commit();
         };
         stage_gp(0);
-        stage_gp(1);
         unsigned own, colmask;
         asmn_masks<SYM>(g, nodemask, masksum, t.ln0, lane, valid, c, own, colmask);
         double acc[NS];
@@ -298,13 +300,12 @@ k_assemble_nodes_pergp(GridDev g, SymGeom sg, ElemRange er, double wg, const dou
         for (int s = 0; s < NS; ++s) acc[s] = 0.;
 #pragma unroll 1
         for (int gp = 0; gp < 8; ++gp) {
-            if (gp < 7) asm volatile("cp.async.wait_group 1;" ::: "memory");
+            if (gp < 7) { stage_gp(gp + 1); asm volatile("cp.async.wait_group 1;" ::: "memory"); }
             else asm volatile("cp.async.wait_group 0;" ::: "memory");
-            __syncthreads();                                             // Gauss point gp is in; the buffer of gp-1 has been read
-            if (gp + 2 < 8) stage_gp(gp + 2);
+            __syncthreads();                                             // Gauss point gp is in
             asmn_gauss_point<true, SYM, true>(gp, 0u, Cu, stage + (gp % ASMN_NBUF) * ASMN_BUF_DOUBLES + lane, off, acc);
+            __syncthreads();                                             // its buffer may be refilled (or become the outgoing tile)
         }
-        __syncthreads();                                                 // the buffers become the outgoing tile
         const bool rowfixed = (own >> d) & 1u, ghost_plane = SYM && t.kl < 0;
 #pragma unroll
         for (int s = S0; s < 27; ++s) {

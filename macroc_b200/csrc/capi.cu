@@ -63,8 +63,8 @@ struct macroc_ctx {
     unsigned *tickets = nullptr;                   // [2] last-block tickets of the fused single-rank reductions
     CgFuse fuse_pw = {nullptr, nullptr};           // set by apply_operator for the launch it is about to make
     bool fuse_pw_done = false;
-    int mf_variant = 0, mf_nseg = 0;               // matrix-free apply: 0 z-marching (mf_march.cuh), 1 patch form; segments override (MACROC_MF_*)
-    int asm_variant = 0, asm_colblock = 64, asm_ctas_per_sm = 2;   // element-Jacobian knobs (MACROC_ASM_*)
+    int mf_variant = 0, mf_nseg = 0;               // matrix-free apply: 0 auto, 1 patch form, 2 z-marching (mf_march.cuh); segments override (MACROC_MF_*)
+    int asm_colblock = 64, asm_ctas_per_sm = 2;    // per-GP element-Jacobian knobs (MACROC_ASM_*)   // element-Jacobian knobs (MACROC_ASM_*)
     int sym_R = 0, sym_nseg = 0, sym_variant = 0, sym_hint = 0;   // tuning overrides (MACROC_SYM_R / _NSEG / _VARIANT / _HINT, read once at create)
     bool A_valid = false, mf_ready = false, Asym_valid = false;
     double *Ke = nullptr, *T = nullptr;
@@ -481,7 +481,6 @@ extern "C" int macroc_create(const macroc_config *cfg, int rank, int nranks, con
     if (const char *v = getenv("MACROC_SYM_HINT")) c->sym_hint = atoi(v);
     if (const char *v = getenv("MACROC_MF_VARIANT")) c->mf_variant = atoi(v);
     if (const char *v = getenv("MACROC_MF_NSEG")) c->mf_nseg = atoi(v);
-    if (const char *v = getenv("MACROC_ASM_VARIANT")) c->asm_variant = atoi(v);
     if (const char *v = getenv("MACROC_ASM_COLBLOCK")) c->asm_colblock = atoi(v);
     if (const char *v = getenv("MACROC_ASM_CTAS")) c->asm_ctas_per_sm = atoi(v);
     if (cfg->device >= 0) c->device = cfg->device;
@@ -1000,21 +999,6 @@ static int launch_assemble_elements(macroc_ctx *c, bool per_gp, double2 *A, int6
 {
     const int64_t tpp = SYM ? sym_tiles_per_plane(c->g, c->sg) : std::max<int64_t>(1, (c->g.npl + TILE_NODES - 1) / TILE_NODES);
     const int64_t colblock = c->asm_colblock > 0 ? std::min<int64_t>(c->asm_colblock, tpp) : tpp;
-    if (c->asm_variant == 1) {
-        // the element-centric kernel of round 2's first half (24 warps, shared-memory reduction rounds): kept for the A/B
-        const int smem = per_gp ? ASM_SMEM_PER_GP : ASM_SMEM_UNIFORM;     // per-GP: + two staging buffers for the tangents
-        static bool configured[64] = {false};                     // function attributes are per device
-        if (!configured[c->device & 63]) {
-            CU(c, cudaFuncSetAttribute(k_assemble_elements<true, SYM>, cudaFuncAttributeMaxDynamicSharedMemorySize, ASM_SMEM_PER_GP));
-            CU(c, cudaFuncSetAttribute(k_assemble_elements<false, SYM>, cudaFuncAttributeMaxDynamicSharedMemorySize, ASM_SMEM_UNIFORM));
-            configured[c->device & 63] = true;
-        }
-        const int blocks = (int)std::min<int64_t>(tile_hi - tile_lo, 148);
-        if (per_gp) k_assemble_elements<true, SYM><<<blocks, ASM_THREADS, smem, c->stream>>>(c->g, c->sg, c->er, c->geo.wg, c->ctan, c->nodemask, A, c->vec[V_DINV], tile_lo, tile_hi, tpp, colblock, 1);
-        else k_assemble_elements<false, SYM><<<blocks, ASM_THREADS, smem, c->stream>>>(c->g, c->sg, c->er, c->geo.wg, c->ctan, c->nodemask, A, c->vec[V_DINV], tile_lo, tile_hi, tpp, colblock, 1);
-        c->launches++;
-        return MACROC_OK;
-    }
     // node-centric kernels (assembly_node.cuh)
     static bool configured[64] = {false};
     if (!configured[c->device & 63]) {
@@ -1170,6 +1154,29 @@ static int spmv_sym_launch(macroc_ctx *c, double *p, double *w, int first, int c
 
 // w = A p on the context's stream; p's halo is exchanged on comm_stream while
 // the rows that do not touch a ghost plane are computed.
+// z-marching matrix-free apply: the segment count whose slowest CTA marches through the fewest planes (a segment costs
+// its planes + 2), and whether the form pays at all: on small grids the segments get so short that the two extra planes
+// dominate, and the patch form (k_apply_mf3d) is used (mf_variant: 0 auto, 1 patch form, 2 marching form).
+static int mf_march_segments(const macroc_ctx *c, int nz)
+{
+    const int bx = (c->g.NX + MZ_BX - 1) / MZ_BX, by = (c->g.NY + MZ_BY - 1) / MZ_BY, slots = 148 * 3;
+    int nseg = 1;
+    int64_t best = INT64_MAX;
+    for (int q = 1; q <= std::min(nz, 64); ++q) {
+        const int64_t items = (int64_t)bx * by * q, rounds = (items + slots - 1) / slots;
+        const int64_t cost = rounds * ((nz + q - 1) / q + 2);
+        if (cost < best) { best = cost; nseg = q; }
+    }
+    return nseg;
+}
+static bool mf_use_march(const macroc_ctx *c, int k0, int k1)
+{
+    if (c->mf_variant == 1) return false;
+    if (c->mf_variant == 2) return true;
+    const int nz = k1 - k0, nseg = mf_march_segments(c, nz);
+    return (nz + nseg - 1) / nseg >= 6;
+}
+
 static int apply_operator(macroc_ctx *c, int op, double *p, double *w, bool with_dot, const int *done,
                           bool fuse_pw_scalars = false, int *nparts_out = nullptr)
 {
@@ -1223,19 +1230,12 @@ static int apply_operator(macroc_ctx *c, int op, double *p, double *w, bool with
                 default: blocks = spmv_sym_launch<8, 3, 8>(c, p, w, (int)first, (int)count, c->partial + nparts, with_dot, done); break;
             }
             if (blocks < 0) { rc_run = MACROC_ERR_CUDA; return; }
-        } else if (mf && c->mf_variant == 0) {
-            // z-marching form: work items = column blocks x z segments, dealt round-robin to the resident CTAs; pick the
-            // segment count whose slowest CTA marches through the fewest planes (a segment costs its planes + 2)
+        } else if (mf && mf_use_march(c, (int)(first / g.npl), (int)((first + count) / g.npl))) {
+            // z-marching form: work items = column blocks x z segments, dealt round-robin to the resident CTAs
             const int k0 = (int)(first / g.npl), k1 = (int)((first + count) / g.npl);
             const int bx = (g.NX + MZ_BX - 1) / MZ_BX, by = (g.NY + MZ_BY - 1) / MZ_BY, nz = k1 - k0;
             const int slots = 148 * 3;
-            int nseg = 1;
-            int64_t best = INT64_MAX;
-            for (int q = 1; q <= std::min(nz, 64); ++q) {
-                const int64_t items = (int64_t)bx * by * q, rounds = (items + slots - 1) / slots;
-                const int64_t cost = rounds * ((nz + q - 1) / q + 2);
-                if (cost < best) { best = cost; nseg = q; }
-            }
+            int nseg = mf_march_segments(c, nz);
             if (c->mf_nseg > 0) nseg = std::min(c->mf_nseg, nz);
             blocks = (int)std::min<int64_t>((int64_t)bx * by * nseg, slots);
             static bool mz_configured[64] = {false};
@@ -1274,8 +1274,9 @@ static int apply_operator(macroc_ctx *c, int op, double *p, double *w, bool with
             // an odd grid: the tile -> CTA map must not be periodic in the 8 x-tiles of a row, or the
             // CTAs that always get a boundary column finish last
             blocks = (int)std::min<int64_t>(ntile, 148 * 6 - 1);
-            if (with_dot) k_apply_mf3d<true><<<blocks, MF_THREADS, MF_SMEM, c->stream>>>(g, c->T, c->nodemask, p, w, k0, k1, tiles_x, tiles_y, c->partial + nparts, done);
-            else k_apply_mf3d<false><<<blocks, MF_THREADS, MF_SMEM, c->stream>>>(g, c->T, c->nodemask, p, w, k0, k1, tiles_x, tiles_y, c->partial + nparts, done);
+            if (with_dot) k_apply_mf3d<true><<<blocks, MF_THREADS, MF_SMEM, c->stream>>>(g, c->T, c->nodemask, p, w, k0, k1, tiles_x, tiles_y, c->partial + nparts, done, c->fuse_pw);
+            else k_apply_mf3d<false><<<blocks, MF_THREADS, MF_SMEM, c->stream>>>(g, c->T, c->nodemask, p, w, k0, k1, tiles_x, tiles_y, c->partial + nparts, done, CgFuse{nullptr, nullptr});
+            if (with_dot && c->fuse_pw.ticket) c->fuse_pw_done = true;
             c->launches++;
         } else {
             blocks = spmv_launch(c, p, w, first, count, c->partial + nparts, with_dot, done);

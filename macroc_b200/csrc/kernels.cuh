@@ -81,6 +81,68 @@ __device__ __forceinline__ double block_sum(double v, double *sm)
 }
 
 // ---------------------------------------------------------------------------
+// KSPCG scalar bookkeeping (used by the vector kernels further down and by the operator kernels' fused reductions)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void cg_scalars_pw_body(CgScalars *s, double pw)
+{
+    // KSPSolve_CG: KSPCheckDot(dpi) -> KSP_DIVERGED_NANORINF; dpi == 0 or a sign change against the
+    // previous dpi -> KSP_DIVERGED_INDEFINITE_MAT
+    const double old = s->pw;
+    const int i = s->its;
+    s->pw = pw;
+    s->its += 1;                               // ksp->its = i+1 at the top of the loop body
+    if (!isfinite(pw)) { s->done = 1; s->reason = -9; }
+    else if (pw == 0. || (i > 0 && ((pw > 0.) != (old > 0.)))) { s->done = 1; s->reason = -10; }
+}
+
+__device__ __forceinline__ void cg_scalars_iter_body(CgScalars *s, double zz, double zr)
+{
+    double dp = sqrt(zz);
+    s->dp = dp;
+    if (!isfinite(dp) || !isfinite(zr)) { s->done = 1; s->reason = -9; return; }      // KSP_DIVERGED_NANORINF
+    if (dp <= s->ttol) { s->done = 1; s->reason = dp <= s->abstol ? 3 : 2; return; }
+    if (dp >= s->dtol * s->dp0) { s->done = 1; s->reason = -4; return; }
+    if (s->its >= s->maxits) { s->done = 1; s->reason = -3; return; }
+    s->betaold = s->beta;
+    s->beta = zr;
+    if (zr < 0.) { s->done = 1; s->reason = -8; return; }             // KSP_DIVERGED_INDEFINITE_PC
+    if (s->beta == 0.) { s->its += 1; s->done = 1; s->reason = 3; }   // KSP_CONVERGED_ATOL at the next top
+}
+
+// Single rank: the reduction of the per-block partials needs no launch of its own.  The block that draws the last
+// ticket folds all partials in a fixed order (bit-reproducible for a given grid) and updates the CG scalars; every
+// other block has read what it needs of them long before (it draws its ticket after its work).  All threads of a
+// block call this after thread 0 has written the block's partial(s).  NV = 1: p.w, NV = 2: (z.z, z.r).
+struct CgFuse {
+    CgScalars *sc;
+    unsigned *ticket;            // nullptr: not fused (several ranks, or a caller that wants the plain sums)
+};
+template <int NW, int NV>
+__device__ __forceinline__ void cg_last_block(const double *partial, int nblk, const CgFuse &f, double *sm /* NW doubles */)
+{
+    __shared__ unsigned s_last;
+    if (threadIdx.x == 0) {
+        __threadfence();                                   // the partial before the ticket
+        s_last = atomicAdd(f.ticket, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!s_last) return;                                   // block-uniform
+    __threadfence();
+    double v0 = 0., v1 = 0.;
+    for (int q = threadIdx.x; q < nblk; q += blockDim.x) {
+        v0 += __ldcg(partial + q);
+        if (NV == 2) v1 += __ldcg(partial + nblk + q);
+    }
+    v0 = block_sum<NW>(v0, sm);
+    if (NV == 2) v1 = block_sum<NW>(v1, sm);
+    if (threadIdx.x == 0) {
+        *f.ticket = 0;
+        if (NV == 1) cg_scalars_pw_body(f.sc, v0);
+        else cg_scalars_iter_body(f.sc, v0, v1);
+    }
+}
+
+// ---------------------------------------------------------------------------
 // Element constants
 // ---------------------------------------------------------------------------
 
@@ -314,7 +376,7 @@ template <bool DOT>
 __global__ void __launch_bounds__(MF_THREADS, 3)
 k_apply_mf3d(GridDev g, const double *__restrict__ Tg, const uint8_t *__restrict__ nodemask,
              const double *__restrict__ x, double *__restrict__ y,
-             int k0, int k1, int tiles_x, int tiles_y, double *__restrict__ partial, const int *__restrict__ done)
+             int k0, int k1, int tiles_x, int tiles_y, double *__restrict__ partial, const int *__restrict__ done, CgFuse fuse)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double(*sx)[MF_PATCH] = reinterpret_cast<double(*)[MF_PATCH]>(smem_raw);
@@ -438,6 +500,7 @@ k_apply_mf3d(GridDev g, const double *__restrict__ Tg, const uint8_t *__restrict
     if (DOT) {
         double s = block_sum<MF_THREADS / 32>(dot, sm);
         if (threadIdx.x == 0) partial[blockIdx.x] = s;
+        if (fuse.ticket) cg_last_block<MF_THREADS / 32, 1>(partial, gridDim.x, fuse, sm);
     }
 }
 
@@ -784,65 +847,6 @@ __device__ __forceinline__ void cg_scalars_init_body(CgScalars *s, double zz, do
 __global__ void k_cg_scalars_init(CgScalars *s, const double *sums /* zz, zr */)
 {
     cg_scalars_init_body(s, sums[0], sums[1]);
-}
-
-__device__ __forceinline__ void cg_scalars_pw_body(CgScalars *s, double pw)
-{
-    // KSPSolve_CG: KSPCheckDot(dpi) -> KSP_DIVERGED_NANORINF; dpi == 0 or a sign change against the
-    // previous dpi -> KSP_DIVERGED_INDEFINITE_MAT
-    const double old = s->pw;
-    const int i = s->its;
-    s->pw = pw;
-    s->its += 1;                               // ksp->its = i+1 at the top of the loop body
-    if (!isfinite(pw)) { s->done = 1; s->reason = -9; }
-    else if (pw == 0. || (i > 0 && ((pw > 0.) != (old > 0.)))) { s->done = 1; s->reason = -10; }
-}
-
-__device__ __forceinline__ void cg_scalars_iter_body(CgScalars *s, double zz, double zr)
-{
-    double dp = sqrt(zz);
-    s->dp = dp;
-    if (!isfinite(dp) || !isfinite(zr)) { s->done = 1; s->reason = -9; return; }      // KSP_DIVERGED_NANORINF
-    if (dp <= s->ttol) { s->done = 1; s->reason = dp <= s->abstol ? 3 : 2; return; }
-    if (dp >= s->dtol * s->dp0) { s->done = 1; s->reason = -4; return; }
-    if (s->its >= s->maxits) { s->done = 1; s->reason = -3; return; }
-    s->betaold = s->beta;
-    s->beta = zr;
-    if (zr < 0.) { s->done = 1; s->reason = -8; return; }             // KSP_DIVERGED_INDEFINITE_PC
-    if (s->beta == 0.) { s->its += 1; s->done = 1; s->reason = 3; }   // KSP_CONVERGED_ATOL at the next top
-}
-
-// Single rank: the reduction of the per-block partials needs no launch of its own.  The block that draws the last
-// ticket folds all partials in a fixed order (bit-reproducible for a given grid) and updates the CG scalars; every
-// other block has read what it needs of them long before (it draws its ticket after its work).  All threads of a
-// block call this after thread 0 has written the block's partial(s).  NV = 1: p.w, NV = 2: (z.z, z.r).
-struct CgFuse {
-    CgScalars *sc;
-    unsigned *ticket;            // nullptr: not fused (several ranks, or a caller that wants the plain sums)
-};
-template <int NW, int NV>
-__device__ __forceinline__ void cg_last_block(const double *partial, int nblk, const CgFuse &f, double *sm /* NW doubles */)
-{
-    __shared__ unsigned s_last;
-    if (threadIdx.x == 0) {
-        __threadfence();                                   // the partial before the ticket
-        s_last = atomicAdd(f.ticket, 1u) == gridDim.x - 1;
-    }
-    __syncthreads();
-    if (!s_last) return;                                   // block-uniform
-    __threadfence();
-    double v0 = 0., v1 = 0.;
-    for (int q = threadIdx.x; q < nblk; q += blockDim.x) {
-        v0 += __ldcg(partial + q);
-        if (NV == 2) v1 += __ldcg(partial + nblk + q);
-    }
-    v0 = block_sum<NW>(v0, sm);
-    if (NV == 2) v1 = block_sum<NW>(v1, sm);
-    if (threadIdx.x == 0) {
-        *f.ticket = 0;
-        if (NV == 1) cg_scalars_pw_body(f.sc, v0);
-        else cg_scalars_iter_body(f.sc, v0, v1);
-    }
 }
 
 // p = z + (beta/betaold) p   (first iteration: p = z), z = r*dinv recomputed

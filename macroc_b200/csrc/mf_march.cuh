@@ -225,7 +225,7 @@ k_apply_mf_faces(GridDev g, const double *__restrict__ Tg, const uint8_t *__rest
         const int type = node_class(i, g.NX) + 3 * node_class(j, g.NY) + 9 * node_class(kl + g.zs, g.NZ);
         const double *Tt = Tg + type * 243;
         double a0 = 0., a1 = 0., a2 = 0.;
-#pragma unroll 1
+#pragma unroll 9                                            // nine slots' loads in flight together (the kernel is latency-bound)
         for (int sl = 0; sl < 27; ++sl) {
             const int dx = sl % 3 - 1, dy = (sl / 3) % 3 - 1, dz = sl / 9 - 1;
             const int64_t lj = ln + dx + (int64_t)g.NX * dy + g.npl * dz;
