@@ -230,12 +230,11 @@ k_apply_mf_faces(GridDev g, const double *__restrict__ Tg, const uint8_t *__rest
             const int dx = sl % 3 - 1, dy = (sl / 3) % 3 - 1, dz = sl / 9 - 1;
             const int64_t lj = ln + dx + (int64_t)g.NX * dy + g.npl * dz;
             const bool ok = i + dx >= -1 && i + dx <= g.NX && lj >= -(int64_t)g.G && g.G + lj < g.S;
-            double x0 = 0., x1 = 0., x2 = 0.;
-            if (ok) {
-                const unsigned mk = nodemask[g.G + lj];
-                const double *xp = x + g.G + lj;
-                x0 = (mk & 1u) ? 0. : __ldg(xp); x1 = (mk & 2u) ? 0. : __ldg(xp + g.S); x2 = (mk & 4u) ? 0. : __ldg(xp + 2 * g.S);
-            }
+            // unconditional loads from a clamped index (a load predicated on the mask byte would wait for it)
+            const int64_t idx = g.G + (ok ? lj : ln);
+            const unsigned mk = ok ? (unsigned)nodemask[idx] : 7u;
+            const double v0 = __ldg(x + idx), v1 = __ldg(x + g.S + idx), v2 = __ldg(x + 2 * g.S + idx);
+            const double x0 = (mk & 1u) ? 0. : v0, x1 = (mk & 2u) ? 0. : v1, x2 = (mk & 4u) ? 0. : v2;
             const double *m = Tt + sl * 9;
             a0 = fma(__ldg(m + 2), x2, fma(__ldg(m + 1), x1, fma(__ldg(m + 0), x0, a0)));
             a1 = fma(__ldg(m + 5), x2, fma(__ldg(m + 4), x1, fma(__ldg(m + 3), x0, a1)));
