@@ -38,8 +38,10 @@ constexpr int ASMN_THREADS = ASMN_WARPS * 32;
 constexpr int ASMN_SROW = 33;                               // staged elements per element row
 constexpr int ASMN_CELLS = 4 * ASMN_SROW;                   // (ey, ez) in {j-1, j} x {k-1, k}
 constexpr int ASMN_BUF_DOUBLES = 36 * ASMN_CELLS;           // one Gauss point: 4 752 doubles
-constexpr int ASMN_NBUF = 2;                                // Gauss point gp is integrated while gp+1 lands.  (A ring of three with one barrier
-                                                            // per Gauss point needs 114.6 KB: one CTA per SM, 74 ms instead of 51.5.)
+constexpr int ASMN_NBUF = 2;                                // Gauss point gp is integrated while gp+1 lands.  (Measured and rejected: a ring of three
+                                                            // with one barrier per Gauss point needs 114.6 KB = one CTA per SM, 74 ms instead of 51.5; no
+                                                            // staging at all -- tangents through L1 with prefetch.global.L1 one Gauss point ahead, no
+                                                            // barrier -- 99.6 ms: long scoreboard 5.4 per issue, L1 hit rate 63 %.)
 constexpr int ASMN_SMEM_PER_GP = ASMN_NBUF * ASMN_BUF_DOUBLES * 8 + ASMN_CELLS * 4;   // 76 560 B: two CTAs per SM
 constexpr int ASMU_WARPS = 4, ASMU_CTAS_PER_SM = 5;         // uniform tangent: 20 independent warps per SM
 
@@ -327,113 +329,6 @@ k_assemble_nodes_pergp(GridDev g, SymGeom sg, ElemRange er, double wg, const dou
         }
     }
     if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-}
-
-// ---- tangents per Gauss point, second form: no staging ------------------------------------------------------
-// The same CTA-per-tile job layout, but the nine warps never meet: every thread reads the nine tangent entries of its
-// (a, Gauss point) straight from global memory through L1 (the 9 warps of the tile and the two x-adjacent lanes share the
-// lines), the lines of the next Gauss point are requested one Gauss point ahead with prefetch.global.L1, and the 27
-// entries leave the registers with 8-byte stores like in the uniform kernel.  No shared memory, no barrier.
-template <bool SYM>
-__global__ void __launch_bounds__(ASMN_THREADS, 2)
-k_assemble_nodes_pergp_l1(GridDev g, SymGeom sg, ElemRange er, double wg, const double *__restrict__ ctan_gp,
-                          const uint8_t *__restrict__ nodemask, const uint8_t *__restrict__ masksum, double2 *__restrict__ A,
-                          double *__restrict__ dinv, int64_t tile_lo, int64_t tile_hi, int64_t tpp, int64_t colblock)
-{
-    constexpr int NS = SYM ? 14 : 27, S0 = SYM ? 13 : 0;
-    constexpr int TILE_D = SYM ? SYM_TILE_DOUBLES : TILE_DOUBLES;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int d = warp / 3, c = warp - 3 * d, e9 = warp;
-    const int64_t per_layer = er.nex * er.ney;
-    unsigned eoff[3][3];                                                   // element-array offset of C[voigt(d,p)][voigt(c,q)] (36 ne_ext < 2^32: checked by the host)
-#pragma unroll
-    for (int p = 0; p < 3; ++p)
-#pragma unroll
-        for (int q = 0; q < 3; ++q) eoff[p][q] = (unsigned)(((d == p) ? d : d + p + 2) * 6 + ((c == q) ? c : c + q + 2)) * (unsigned)er.ne_ext;
-    const int64_t ntl = tile_hi - tile_lo;
-    const int64_t mtot = (ntl + tpp - 1) / tpp, ncb = (tpp + colblock - 1) / colblock;
-    const int64_t vper = colblock * mtot, vend = ncb * vper;
-    for (int64_t v = blockIdx.x; v < vend; v += gridDim.x) {
-        const int64_t cb = v / vper, rem = v - cb * vper;
-        const int64_t vrow = rem / colblock;
-        const int64_t col = cb * colblock + (rem - vrow * colblock);
-        const int64_t tile = tile_lo + col + vrow * tpp;
-        if (col >= tpp || tile >= tile_hi) continue;                       // block-uniform
-        const AsmTile t = asmn_decode<SYM>(g, sg, tile, tpp, lane);
-        const bool valid = lane < t.nvalid;
-        const int k = t.kl + g.zs;
-        // the element in which the node is local node a (0 and a cleared bit in ex when this rank does not hold it)
-        int ie[8];
-        unsigned ex = 0;
-#pragma unroll
-        for (int a = 0; a < 8; ++a) {
-            const int ei = t.i - node_px(a), ej = t.j - node_py(a), ek = k - node_pz(a);
-            const bool ok = valid && ei >= 0 && ei < g.NX - 1 && ej >= 0 && ej < g.NY - 1 && ek >= 0 && ek < g.NZ - 1 && ek >= er.ezs &&
-                            ek < er.ezs + er.nez_ext;
-            ie[a] = ok ? (int)((int64_t)(ek - er.ezs) * per_layer + ei + er.nex * (int64_t)ej) : 0;
-            if (ok) ex |= 1u << a;
-        }
-        // prefetch plan: thread = (tangent entry, element row); the row's 33 elements span three 128-byte lines.  The row
-        // starts at the element in which lane 0's node is the px = 1 node (px = 0 on the x = 0 face); -1: no such row
-        const int pf_entry = threadIdx.x >> 2;
-        int pf_elem = -1;
-#pragma unroll
-        for (int rr = 0; rr < 4; ++rr) {
-            const int a1 = local_node_of_pos(1, 1 - (rr & 1), 1 - (rr >> 1)), a0 = local_node_of_pos(0, 1 - (rr & 1), 1 - (rr >> 1));
-            const int cand = ((ex >> a1) & 1u) ? ie[a1] : (((ex >> a0) & 1u) ? ie[a0] : -1);
-            const int first = __shfl_sync(0xffffffffu, cand, 0);
-            if (rr == (int)(threadIdx.x & 3)) pf_elem = first;
-        }
-        auto prefetch_gp = [&](int gp) {
-            if (threadIdx.x < 144 && pf_elem >= 0) {
-                const double *ptr = ctan_gp + ((int64_t)gp * 36 + pf_entry) * er.ne_ext + pf_elem;
-                const int64_t lim = er.ne_ext - pf_elem - 1;
-                asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr));
-                asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr + (lim < 16 ? lim : 16)));
-                asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr + (lim < 32 ? lim : 32)));
-            }
-        };
-        unsigned own, colmask;
-        asmn_masks<SYM>(g, nodemask, masksum, t.ln0, lane, valid, c, own, colmask);
-        double acc[NS];
-#pragma unroll
-        for (int s = 0; s < NS; ++s) acc[s] = 0.;
-        prefetch_gp(0);
-#pragma unroll 1
-        for (int gp = 0; gp < 8; ++gp) {
-            if (gp < 7) prefetch_gp(gp + 1);
-            const double *base = ctan_gp + (int64_t)gp * 36 * er.ne_ext;
-            const double2 *h2 = reinterpret_cast<const double2 *>(&c_dsh[gp][0][0]);
-            double hb[24];
-#pragma unroll
-            for (int q = 0; q < 12; ++q) { const double2 tt = h2[q]; hb[2 * q] = tt.x; hb[2 * q + 1] = tt.y; }
-#pragma unroll
-            for (int a = 0; a < 8; ++a) {
-                const double *ck = base + ie[a];
-                const double h0 = hb[3 * a], h1 = hb[3 * a + 1], h2a = hb[3 * a + 2];
-                double T[3];
-#pragma unroll
-                for (int q = 0; q < 3; ++q) T[q] = fma(h2a, __ldg(ck + eoff[2][q]), fma(h1, __ldg(ck + eoff[1][q]), h0 * __ldg(ck + eoff[0][q])));
-                if (!((ex >> a) & 1u)) T[0] = T[1] = T[2] = 0.;
-#pragma unroll
-                for (int b = 0; b < 8; ++b) {
-                    if (SYM && node_rank(b) < node_rank(a)) continue;
-                    const int s = slot_of(a, b) - S0;
-                    acc[s] = fma(T[0], hb[3 * b], fma(T[1], hb[3 * b + 1], fma(T[2], hb[3 * b + 2], acc[s])));
-                }
-            }
-        }
-        const bool rowfixed = (own >> d) & 1u, ghost_plane = SYM && t.kl < 0;
-        double *At = reinterpret_cast<double *>(A) + tile * (int64_t)TILE_D + 2 * lane;
-#pragma unroll
-        for (int s = S0; s < 27; ++s) {
-            const double val = asmn_entry<SYM>(s, acc[s - S0], wg, valid, rowfixed, colmask, d == c, ghost_plane);
-            if (s == 13 && d == c && valid && !ghost_plane) dinv[d * g.S + g.G + t.ln0 + lane] = val != 0. ? 1. / val : 1.;
-            const int kk = 9 * (s - S0) + e9;
-            At[(kk >> 1) * (2 * TILE_NODES) + (kk & 1)] = val;
-        }
-        if (!SYM && e9 == 8) At[(PAIRS - 1) * (2 * TILE_NODES) + 1] = 0.;  // entry 243: padding
-    }
 }
 
 }  // namespace macroc

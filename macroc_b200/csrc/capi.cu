@@ -64,7 +64,7 @@ struct macroc_ctx {
     CgFuse fuse_pw = {nullptr, nullptr};           // set by apply_operator for the launch it is about to make
     bool fuse_pw_done = false;
     int mf_variant = 0, mf_nseg = 0;               // matrix-free apply: 0 auto, 1 patch form, 2 z-marching (mf_march.cuh); segments override (MACROC_MF_*)
-    int asm_colblock = 64, asm_ctas_per_sm = 2, asm_pergp_variant = 0;    // per-GP element-Jacobian knobs (MACROC_ASM_*)   // element-Jacobian knobs (MACROC_ASM_*)
+    int asm_colblock = 64, asm_ctas_per_sm = 2;    // per-GP element-Jacobian knobs (MACROC_ASM_*)   // element-Jacobian knobs (MACROC_ASM_*)
     int sym_R = 0, sym_nseg = 0, sym_variant = 0, sym_hint = 0;   // tuning overrides (MACROC_SYM_R / _NSEG / _VARIANT / _HINT, read once at create)
     bool A_valid = false, mf_ready = false, Asym_valid = false;
     double *Ke = nullptr, *T = nullptr;
@@ -483,7 +483,6 @@ extern "C" int macroc_create(const macroc_config *cfg, int rank, int nranks, con
     if (const char *v = getenv("MACROC_MF_NSEG")) c->mf_nseg = atoi(v);
     if (const char *v = getenv("MACROC_ASM_COLBLOCK")) c->asm_colblock = atoi(v);
     if (const char *v = getenv("MACROC_ASM_CTAS")) c->asm_ctas_per_sm = atoi(v);
-    if (const char *v = getenv("MACROC_ASM_PERGP_VARIANT")) c->asm_pergp_variant = atoi(v);
     if (cfg->device >= 0) c->device = cfg->device;
     else if (cudaGetDevice(&c->device) != cudaSuccess) c->device = 0;
 #define CUC(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { g_last_error = std::string(#call) + " -> " + cudaGetErrorString(_e); ctx_free(c); return MACROC_ERR_CUDA; } } while (0)
@@ -1009,10 +1008,7 @@ static int launch_assemble_elements(macroc_ctx *c, bool per_gp, double2 *A, int6
     if (per_gp) {
         // exactly the resident CTAs, so that neighbouring rows and planes are in flight together and share their tangents in L2
         const int blocks = (int)std::min<int64_t>(tile_hi - tile_lo, 148 * std::max(1, c->asm_ctas_per_sm));
-        if (c->asm_pergp_variant == 1 && c->er.ne_ext * 36 < ((int64_t)1 << 32))
-            k_assemble_nodes_pergp_l1<SYM><<<blocks, ASMN_THREADS, 0, c->stream>>>(c->g, c->sg, c->er, c->geo.wg, c->ctan, c->nodemask, c->masksum, A, c->vec[V_DINV], tile_lo, tile_hi, tpp, colblock);
-        else
-            k_assemble_nodes_pergp<SYM><<<blocks, ASMN_THREADS, ASMN_SMEM_PER_GP, c->stream>>>(c->g, c->sg, c->er, c->geo.wg, c->ctan, c->nodemask, c->masksum, A, c->vec[V_DINV], tile_lo, tile_hi, tpp, colblock);
+        k_assemble_nodes_pergp<SYM><<<blocks, ASMN_THREADS, ASMN_SMEM_PER_GP, c->stream>>>(c->g, c->sg, c->er, c->geo.wg, c->ctan, c->nodemask, c->masksum, A, c->vec[V_DINV], tile_lo, tile_hi, tpp, colblock);
     } else {
         const int blocks = (int)std::min<int64_t>(cdiv64((tile_hi - tile_lo) * 9, ASMU_WARPS), 148 * ASMU_CTAS_PER_SM);
         k_assemble_nodes_uniform<SYM><<<blocks, ASMU_WARPS * 32, 0, c->stream>>>(c->g, c->sg, c->er, c->geo.wg, c->nodemask, c->masksum, A, c->vec[V_DINV], tile_lo, tile_hi, tpp);
@@ -1278,10 +1274,20 @@ static int apply_operator(macroc_ctx *c, int op, double *p, double *w, bool with
             // an odd grid: the tile -> CTA map must not be periodic in the 8 x-tiles of a row, or the
             // CTAs that always get a boundary column finish last
             blocks = (int)std::min<int64_t>(ntile, 148 * 6 - 1);
-            if (with_dot) k_apply_mf3d<true><<<blocks, MF_THREADS, MF_SMEM, c->stream>>>(g, c->T, c->nodemask, p, w, k0, k1, tiles_x, tiles_y, c->partial + nparts, done, c->fuse_pw);
-            else k_apply_mf3d<false><<<blocks, MF_THREADS, MF_SMEM, c->stream>>>(g, c->T, c->nodemask, p, w, k0, k1, tiles_x, tiles_y, c->partial + nparts, done, CgFuse{nullptr, nullptr});
+            // the nodes on a face of the box first (their partials come first), then the patch kernel for the rest
+            const int64_t nface = mf_face_count(g, k0, k1);
+            const int fblocks = (int)std::min<int64_t>(cdiv64(nface, 128), 148 * 16);
+            double *pbase = c->partial + nparts;
+            if (fblocks > 0) {
+                if (with_dot) k_apply_mf_faces<true><<<fblocks, 128, 0, c->stream>>>(g, c->T, c->nodemask, p, w, k0, k1, pbase, done);
+                else k_apply_mf_faces<false><<<fblocks, 128, 0, c->stream>>>(g, c->T, c->nodemask, p, w, k0, k1, pbase, done);
+                c->launches++;
+            }
+            if (with_dot) k_apply_mf3d<true><<<blocks, MF_THREADS, MF_SMEM, c->stream>>>(g, c->T, c->nodemask, p, w, k0, k1, tiles_x, tiles_y, pbase, fblocks, done, c->fuse_pw);
+            else k_apply_mf3d<false><<<blocks, MF_THREADS, MF_SMEM, c->stream>>>(g, c->T, c->nodemask, p, w, k0, k1, tiles_x, tiles_y, pbase, fblocks, done, CgFuse{nullptr, nullptr});
             if (with_dot && c->fuse_pw.ticket) c->fuse_pw_done = true;
             c->launches++;
+            blocks += fblocks;
         } else {
             blocks = spmv_launch(c, p, w, first, count, c->partial + nparts, with_dot, done);
         }

@@ -373,10 +373,11 @@ constexpr int MF_THREADS = MF_TX * MF_TZ;
 constexpr int MF_SMEM = 3 * MF_PATCH * (int)sizeof(double);   // the staged patch of M x
 
 template <bool DOT>
-__global__ void __launch_bounds__(MF_THREADS, 3)
+__global__ void __launch_bounds__(MF_THREADS, 2)
 k_apply_mf3d(GridDev g, const double *__restrict__ Tg, const uint8_t *__restrict__ nodemask,
              const double *__restrict__ x, double *__restrict__ y,
-             int k0, int k1, int tiles_x, int tiles_y, double *__restrict__ partial, const int *__restrict__ done, CgFuse fuse)
+             int k0, int k1, int tiles_x, int tiles_y, double *__restrict__ partial /* all partials of this apply */,
+             int part0 /* this kernel's first slot (the face kernel's come before) */, const int *__restrict__ done, CgFuse fuse)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double(*sx)[MF_PATCH] = reinterpret_cast<double(*)[MF_PATCH]>(smem_raw);
@@ -423,63 +424,40 @@ k_apply_mf3d(GridDev g, const double *__restrict__ Tg, const uint8_t *__restrict
         const bool col_valid = i < g.NX && kl < k1;
         const int cx = node_class(i, g.NX), cz = node_class(kl + g.zs, g.NZ);
         int type[MF_TY];
-        bool interior = true;
 #pragma unroll
         for (int jj = 0; jj < MF_TY; ++jj) {
             const int j = j0 + jj;
             type[jj] = (col_valid && j < g.NY) ? cx + 3 * node_class(j, g.NY) + 9 * cz : 13;
-            interior = interior && type[jj] == 13;
         }
         double acc[MF_TY][3];
 #pragma unroll
         for (int jj = 0; jj < MF_TY; ++jj) acc[jj][0] = acc[jj][1] = acc[jj][2] = 0.;
         const int cbase = ((tz + 1) * MF_PY) * MF_PX + tx + 1;          // patch row py = 0 of this column
-        if (__all_sync(0xffffffffu, interior)) {
+        // every node takes the interior stencil here; the nodes on a face of the box (another class) are skipped below and
+        // done by k_apply_mf_faces (mf_march.cuh)
 #pragma unroll
-            for (int dz = -1; dz <= 1; ++dz)
+        for (int dz = -1; dz <= 1; ++dz)
 #pragma unroll
-                for (int py = 0; py < MF_PY; ++py)
+            for (int py = 0; py < MF_PY; ++py)
 #pragma unroll
-                    for (int dx = -1; dx <= 1; ++dx) {
-                        const int o = cbase + (dz * MF_PY + py) * MF_PX + dx;
-                        const double x0 = sx[0][o], x1 = sx[1][o], x2 = sx[2][o];
+                for (int dx = -1; dx <= 1; ++dx) {
+                    const int o = cbase + (dz * MF_PY + py) * MF_PX + dx;
+                    const double x0 = sx[0][o], x1 = sx[1][o], x2 = sx[2][o];
 #pragma unroll
-                        for (int jj = 0; jj < MF_TY; ++jj) {
-                            const int ddy = py - 1 - jj;
-                            if (ddy < -1 || ddy > 1) continue;
-                            const int ct = 13 * 243 + ((dz + 1) * 9 + (ddy + 1) * 3 + (dx + 1)) * 9;
-                            acc[jj][0] = fma(c_T[ct + 0], x0, acc[jj][0]); acc[jj][0] = fma(c_T[ct + 1], x1, acc[jj][0]); acc[jj][0] = fma(c_T[ct + 2], x2, acc[jj][0]);
-                            acc[jj][1] = fma(c_T[ct + 3], x0, acc[jj][1]); acc[jj][1] = fma(c_T[ct + 4], x1, acc[jj][1]); acc[jj][1] = fma(c_T[ct + 5], x2, acc[jj][1]);
-                            acc[jj][2] = fma(c_T[ct + 6], x0, acc[jj][2]); acc[jj][2] = fma(c_T[ct + 7], x1, acc[jj][2]); acc[jj][2] = fma(c_T[ct + 8], x2, acc[jj][2]);
-                        }
+                    for (int jj = 0; jj < MF_TY; ++jj) {
+                        const int ddy = py - 1 - jj;
+                        if (ddy < -1 || ddy > 1) continue;
+                        const int ct = 13 * 243 + ((dz + 1) * 9 + (ddy + 1) * 3 + (dx + 1)) * 9;
+                        acc[jj][0] = fma(c_T[ct + 0], x0, acc[jj][0]); acc[jj][0] = fma(c_T[ct + 1], x1, acc[jj][0]); acc[jj][0] = fma(c_T[ct + 2], x2, acc[jj][0]);
+                        acc[jj][1] = fma(c_T[ct + 3], x0, acc[jj][1]); acc[jj][1] = fma(c_T[ct + 4], x1, acc[jj][1]); acc[jj][1] = fma(c_T[ct + 5], x2, acc[jj][1]);
+                        acc[jj][2] = fma(c_T[ct + 6], x0, acc[jj][2]); acc[jj][2] = fma(c_T[ct + 7], x1, acc[jj][2]); acc[jj][2] = fma(c_T[ct + 8], x2, acc[jj][2]);
                     }
-        } else {
-            // boundary classes: per-node class offsets into the global copy of the table (L1
-            // resident; lanes of one class broadcast, divergent constant-bank reads would serialise)
-#pragma unroll 1
-            for (int dz = -1; dz <= 1; ++dz)
-#pragma unroll 1
-                for (int py = 0; py < MF_PY; ++py)
-#pragma unroll
-                    for (int dx = -1; dx <= 1; ++dx) {
-                        const int o = cbase + (dz * MF_PY + py) * MF_PX + dx;
-                        const double x0 = sx[0][o], x1 = sx[1][o], x2 = sx[2][o];
-#pragma unroll
-                        for (int jj = 0; jj < MF_TY; ++jj) {
-                            const int ddy = py - 1 - jj;
-                            if (ddy < -1 || ddy > 1) continue;
-                            const double *m = Tg + type[jj] * 243 + ((dz + 1) * 9 + (ddy + 1) * 3 + (dx + 1)) * 9;
-                            acc[jj][0] = fma(__ldg(m + 0), x0, acc[jj][0]); acc[jj][0] = fma(__ldg(m + 1), x1, acc[jj][0]); acc[jj][0] = fma(__ldg(m + 2), x2, acc[jj][0]);
-                            acc[jj][1] = fma(__ldg(m + 3), x0, acc[jj][1]); acc[jj][1] = fma(__ldg(m + 4), x1, acc[jj][1]); acc[jj][1] = fma(__ldg(m + 5), x2, acc[jj][1]);
-                            acc[jj][2] = fma(__ldg(m + 6), x0, acc[jj][2]); acc[jj][2] = fma(__ldg(m + 7), x1, acc[jj][2]); acc[jj][2] = fma(__ldg(m + 8), x2, acc[jj][2]);
-                        }
-                    }
-        }
+                }
         if (col_valid) {
 #pragma unroll
             for (int jj = 0; jj < MF_TY; ++jj) {
                 const int j = j0 + jj;
-                if (j >= g.NY) continue;
+                if (j >= g.NY || type[jj] != 13) continue;
                 const int64_t ln = (int64_t)kl * g.npl + (int64_t)j * g.NX + i;
                 const unsigned own = nodemask[g.G + ln];
                 const int c0 = cbase + (jj + 1) * MF_PX;
@@ -499,8 +477,8 @@ k_apply_mf3d(GridDev g, const double *__restrict__ Tg, const uint8_t *__restrict
     }
     if (DOT) {
         double s = block_sum<MF_THREADS / 32>(dot, sm);
-        if (threadIdx.x == 0) partial[blockIdx.x] = s;
-        if (fuse.ticket) cg_last_block<MF_THREADS / 32, 1>(partial, gridDim.x, fuse, sm);
+        if (threadIdx.x == 0) partial[part0 + blockIdx.x] = s;
+        if (fuse.ticket) cg_last_block<MF_THREADS / 32, 1>(partial, part0 + gridDim.x, fuse, sm);
     }
 }
 

@@ -223,10 +223,18 @@ k_apply_mf_faces(GridDev g, const double *__restrict__ Tg, const uint8_t *__rest
         }
         const int64_t ln = (int64_t)kl * g.npl + (int64_t)j * g.NX + i;
         const int type = node_class(i, g.NX) + 3 * node_class(j, g.NY) + 9 * node_class(kl + g.zs, g.NZ);
+        const unsigned own = nodemask[g.G + ln];
         const double *Tt = Tg + type * 243;
+        // a warp whose nodes are all of one class (the inside of a face) takes the table from the constant bank: the
+        // kernel is bound by load instructions, and these are two thirds of them
+        const unsigned am = __activemask();
+        const int type0 = __shfl_sync(am, type, __ffs(am) - 1);
+        const bool one_class = __all_sync(am, type == type0);
         double a0 = 0., a1 = 0., a2 = 0.;
+        // a node with all three dofs prescribed is an identity row (the bending case fixes the whole x faces, whose
+        // stride-NX neighbourhoods are the expensive ones here): no stencil
 #pragma unroll 9                                            // nine slots' loads in flight together (the kernel is latency-bound)
-        for (int sl = 0; sl < 27; ++sl) {
+        for (int sl = 0; sl < (own == 7u ? 0 : 27); ++sl) {
             const int dx = sl % 3 - 1, dy = (sl / 3) % 3 - 1, dz = sl / 9 - 1;
             const int64_t lj = ln + dx + (int64_t)g.NX * dy + g.npl * dz;
             const bool ok = i + dx >= -1 && i + dx <= g.NX && lj >= -(int64_t)g.G && g.G + lj < g.S;
@@ -235,12 +243,18 @@ k_apply_mf_faces(GridDev g, const double *__restrict__ Tg, const uint8_t *__rest
             const unsigned mk = ok ? (unsigned)nodemask[idx] : 7u;
             const double v0 = __ldg(x + idx), v1 = __ldg(x + g.S + idx), v2 = __ldg(x + 2 * g.S + idx);
             const double x0 = (mk & 1u) ? 0. : v0, x1 = (mk & 2u) ? 0. : v1, x2 = (mk & 4u) ? 0. : v2;
-            const double *m = Tt + sl * 9;
-            a0 = fma(__ldg(m + 2), x2, fma(__ldg(m + 1), x1, fma(__ldg(m + 0), x0, a0)));
-            a1 = fma(__ldg(m + 5), x2, fma(__ldg(m + 4), x1, fma(__ldg(m + 3), x0, a1)));
-            a2 = fma(__ldg(m + 8), x2, fma(__ldg(m + 7), x1, fma(__ldg(m + 6), x0, a2)));
+            if (one_class) {
+                const double *m = c_T + type0 * 243 + sl * 9;
+                a0 = fma(m[2], x2, fma(m[1], x1, fma(m[0], x0, a0)));
+                a1 = fma(m[5], x2, fma(m[4], x1, fma(m[3], x0, a1)));
+                a2 = fma(m[8], x2, fma(m[7], x1, fma(m[6], x0, a2)));
+            } else {
+                const double *m = Tt + sl * 9;
+                a0 = fma(__ldg(m + 2), x2, fma(__ldg(m + 1), x1, fma(__ldg(m + 0), x0, a0)));
+                a1 = fma(__ldg(m + 5), x2, fma(__ldg(m + 4), x1, fma(__ldg(m + 3), x0, a1)));
+                a2 = fma(__ldg(m + 8), x2, fma(__ldg(m + 7), x1, fma(__ldg(m + 6), x0, a2)));
+            }
         }
-        const unsigned own = nodemask[g.G + ln];
         const double *xo = x + g.G + ln;
         const double p0 = __ldg(xo), p1 = __ldg(xo + g.S), p2 = __ldg(xo + 2 * g.S);
         if (own & 1u) a0 = p0;                              // Dirichlet rows are identity rows
