@@ -1,5 +1,6 @@
 """Times the per-element Jacobian kernel (uniform D from constant memory, then per-GP tangents) into the full
-(what 7) and the symmetric (what 17) operator layout; MACROC_ASM_VARIANT=1 selects the element-centric kernel."""
+(what 7) and the symmetric (what 17) operator layout; `check`: both kernels and layouts against the class-stencil fill
+on three grids."""
 import sys
 sys.path.insert(0, ".")
 import numpy as np
