@@ -1159,7 +1159,7 @@ static int spmv_sym_launch(macroc_ctx *c, double *p, double *w, int first, int c
 // dominate, and the patch form (k_apply_mf3d) is used (mf_variant: 0 auto, 1 patch form, 2 marching form).
 static int mf_march_segments(const macroc_ctx *c, int nz)
 {
-    const int bx = (c->g.NX + MZ_BX - 1) / MZ_BX, by = (c->g.NY + MZ_BY - 1) / MZ_BY, slots = 148 * 3;
+    const int bx = (c->g.NX + MZ_BX - 1) / MZ_BX, by = (c->g.NY + MZ_BY - 1) / MZ_BY, slots = 148 * MZ_CTAS;
     int nseg = 1;
     int64_t best = INT64_MAX;
     for (int q = 1; q <= std::min(nz, 64); ++q) {
@@ -1234,7 +1234,7 @@ static int apply_operator(macroc_ctx *c, int op, double *p, double *w, bool with
             // z-marching form: work items = column blocks x z segments, dealt round-robin to the resident CTAs
             const int k0 = (int)(first / g.npl), k1 = (int)((first + count) / g.npl);
             const int bx = (g.NX + MZ_BX - 1) / MZ_BX, by = (g.NY + MZ_BY - 1) / MZ_BY, nz = k1 - k0;
-            const int slots = 148 * 3;
+            const int slots = 148 * MZ_CTAS;
             int nseg = mf_march_segments(c, nz);
             if (c->mf_nseg > 0) nseg = std::min(c->mf_nseg, nz);
             blocks = (int)std::min<int64_t>((int64_t)bx * by * nseg, slots);

@@ -22,9 +22,16 @@
 
 namespace macroc {
 
-constexpr int MZ_BX = 32, MZ_BY = 16, MZ_NY = 4;            // nodes per CTA in x, y; nodes per thread in y
+#ifndef MACROC_MZ_NY
+#define MACROC_MZ_NY 4                                      // measurement builds: -DMACROC_MZ_NY=3 (12-row blocks, four CTAs per SM)
+#endif
+constexpr int MZ_NY = MACROC_MZ_NY;                        // nodes per thread in y
+constexpr int MZ_BX = 32, MZ_BY = 4 * MZ_NY;               // nodes per CTA in x, y (a warp = 8 x-positions x 4 row groups)
+constexpr int MZ_CTAS = MZ_NY == 4 ? 3 : 4;                // resident CTAs per SM (registers)
 constexpr int MZ_THREADS = MZ_BX * MZ_BY / MZ_NY;          // 128
-constexpr int MZ_PITCH = 34;                               // = MZ_BX + 2; the row groups of a half-warp are 4 rows apart: 4 * 34 = 8 (mod 16) doubles, no bank conflicts
+// row pitch >= MZ_BX + 2 with (MZ_NY * pitch) = 8 (mod 16): the row groups of a half-warp fall into disjoint bank halves
+constexpr int MZ_PITCH = MZ_NY == 4 ? 34 : 40;
+static_assert((MZ_NY * MZ_PITCH) % 16 == 8 && MZ_PITCH >= MZ_BX + 2, "bank-conflict-free row pitch");
 constexpr int MZ_ROWS = MZ_BY + 2;
 constexpr int MZ_PLANE = MZ_PITCH * MZ_ROWS;               // doubles per component
 constexpr int MZ_POINTS = (MZ_BX + 2) * MZ_ROWS;           // 612 staged points per plane
@@ -35,7 +42,7 @@ constexpr int MZ_SLOT_BYTES = 3 * MZ_PLANE * 8 + MZ_MASKB;
 constexpr int MZ_SMEM = MZ_SLOTS * MZ_SLOT_BYTES;          // 61 312 B: three CTAs per SM
 
 template <bool DOT>
-__global__ void __launch_bounds__(MZ_THREADS, 3)
+__global__ void __launch_bounds__(MZ_THREADS, MZ_CTAS)
 k_apply_mf_march(GridDev g, const double *__restrict__ Tg, const uint8_t *__restrict__ nodemask, const double *__restrict__ x,
                  double *__restrict__ y, int k0, int k1, int bx, int by, int nseg, double *__restrict__ partial /* all partials of this apply */,
                  int part0 /* this kernel's first slot in it (the face kernel's come before) */, const int *__restrict__ done, CgFuse fuse)
