@@ -43,7 +43,8 @@ constexpr int ASMN_NBUF = 2;                                // Gauss point gp is
                                                             // staging at all -- tangents through L1 with prefetch.global.L1 one Gauss point ahead, no
                                                             // barrier -- 99.6 ms: long scoreboard 5.4 per issue, L1 hit rate 63 %.)
 constexpr int ASMN_SMEM_PER_GP = ASMN_NBUF * ASMN_BUF_DOUBLES * 8 + ASMN_CELLS * 4;   // 76 560 B: two CTAs per SM
-constexpr int ASMU_WARPS = 4, ASMU_CTAS_PER_SM = 5;         // uniform tangent: 20 independent warps per SM
+constexpr int ASMU_WARPS = 4, ASMU_CTAS_PER_SM = 5;         // uniform tangent: 20 independent warps per SM (a sixth CTA for the
+                                                            // symmetric layout, 80 registers: 15.86 ms instead of 16.15 -- not worth a second setting)
 
 __host__ __device__ __forceinline__ constexpr int node_rank(int n) { return node_px(n) + 2 * node_py(n) + 4 * node_pz(n); }
 __host__ __device__ __forceinline__ constexpr int slot_of(int a, int b)
@@ -221,7 +222,7 @@ k_assemble_nodes_uniform(GridDev g, SymGeom sg, ElemRange er, double wg, const u
 
 // ---- tangents per Gauss point ---------------------------------------------------------------------------
 template <bool SYM>
-__global__ void __launch_bounds__(ASMN_THREADS, 2)
+__global__ void __launch_bounds__(ASMN_THREADS, 2)       // (three CTAs per SM for the symmetric layout: 72 registers, spills in the loop, 63 ms instead of 42.6)
 k_assemble_nodes_pergp(GridDev g, SymGeom sg, ElemRange er, double wg, const double *__restrict__ ctan_gp,
                        const uint8_t *__restrict__ nodemask, const uint8_t *__restrict__ masksum, double2 *__restrict__ A,
                        double *__restrict__ dinv, int64_t tile_lo, int64_t tile_hi, int64_t tpp /* tiles per plane (rounded up for the full layout) */,
