@@ -230,10 +230,10 @@ k_assemble_nodes_pergp(GridDev g, SymGeom sg, ElemRange er, double wg, const dou
 {
     constexpr int NS = SYM ? 14 : 27, S0 = SYM ? 13 : 0;
     constexpr int TILE_D = SYM ? SYM_TILE_DOUBLES : TILE_DOUBLES;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    double *stage = reinterpret_cast<double *>(smem_raw);                  // [ASMN_NBUF][36][ASMN_CELLS]
+    extern __shared__ __align__(128) unsigned char smem_asmn[];
+    double *stage = reinterpret_cast<double *>(smem_asmn);                 // [ASMN_NBUF][36][ASMN_CELLS]
     double *tileA = stage;                                                 // the outgoing tile re-uses the buffers
-    int *cell_ie = reinterpret_cast<int *>(smem_raw + ASMN_NBUF * ASMN_BUF_DOUBLES * 8);   // element of a cell, -1 = none
+    int *cell_ie = reinterpret_cast<int *>(smem_asmn + ASMN_NBUF * ASMN_BUF_DOUBLES * 8);   // element of a cell, -1 = none
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int d = warp / 3, c = warp - 3 * d, e9 = warp;
     const int64_t per_layer = er.nex * er.ney;
